@@ -1,0 +1,116 @@
+"""ctypes binding of libfrosting_b200.so (the C ABI in include/frosting_b200.h).
+
+There is no fallback: if the CUDA library is missing this module raises at import of the symbols,
+and every op in this package fails loudly.  PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfrosting_b200.so")
+
+FB200_STATUS_WORDS = 8
+ST_NUM_RENDERED, ST_OVERFLOW, ST_MAX_TILE, ST_NUM_VISIBLE = 0, 1, 2, 3
+TILE = 16
+
+# every symbol include/frosting_b200.h declares
+EXPORTED = [
+    "fb200_abi_version", "fb200_last_error", "fb200_geom_bytes", "fb200_image_bytes",
+    "fb200_binning_bytes", "fb200_forward", "fb200_backward", "fb200_mark_visible",
+    "fb200_mesh_visibility", "fb200_gaussian_mask_from_faces", "fb200_get_layout",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+    ]
+
+
+class Inputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_background", "d_means3D", "d_shs", "d_colors_precomp", "d_opacities", "d_scales",
+        "d_rotations", "d_cov3D_precomp", "d_viewmatrix", "d_projmatrix", "d_campos", "d_visibility")]
+
+
+class Workspace(C.Structure):
+    _fields_ = [
+        ("d_geom", C.c_void_p), ("geom_bytes", C.c_size_t),
+        ("d_image", C.c_void_p), ("image_bytes", C.c_size_t),
+        ("d_binning", C.c_void_p), ("binning_bytes", C.c_size_t),
+        ("binning_capacity", C.c_int64),
+        ("d_status", C.c_void_p),
+    ]
+
+
+class Grads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dopacity", "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh",
+        "d_dL_dscales", "d_dL_drotations")]
+
+
+class Layout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "geom_rec", "geom_depth", "geom_rect", "geom_clamped", "img_final_T", "img_n_contrib",
+        "img_ranges", "img_tile_count", "bin_point_list", "bin_keys")]
+
+
+_lib = None
+
+
+def build_if_needed():
+    """(Re)build the shared library in-tree when sources are newer; needs nvcc only."""
+    from . import build as _build
+    return _build.build()
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            build_if_needed()
+        except Exception as ex:  # no nvcc / compile error: fail loudly, never fall back
+            raise RuntimeError(
+                f"frosting_b200: CUDA library {LIB_PATH} is missing and could not be built ({ex}). "
+                "Run `python -m frosting_b200.build`. There is no CPU fallback.") from ex
+    L = C.CDLL(LIB_PATH)
+    L.fb200_abi_version.restype = C.c_int
+    L.fb200_last_error.restype = C.c_char_p
+    for n in ("fb200_geom_bytes", "fb200_image_bytes", "fb200_binning_bytes"):
+        getattr(L, n).restype = C.c_size_t
+    L.fb200_geom_bytes.argtypes = [C.c_int32]
+    L.fb200_image_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.fb200_binning_bytes.argtypes = [C.c_int64]
+    L.fb200_forward.argtypes = [C.POINTER(Params), C.POINTER(Inputs), C.POINTER(Workspace),
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fb200_backward.argtypes = [C.POINTER(Params), C.POINTER(Inputs), C.POINTER(Workspace),
+                                 C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p]
+    L.fb200_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fb200_mesh_visibility.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p]
+    L.fb200_gaussian_mask_from_faces.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                                 C.c_void_p, C.c_void_p]
+    L.fb200_get_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Layout)]
+    for n in ("fb200_forward", "fb200_backward", "fb200_mark_visible", "fb200_mesh_visibility",
+              "fb200_gaussian_mask_from_faces", "fb200_get_layout"):
+        getattr(L, n).restype = C.c_int
+    if L.fb200_abi_version() != 1:
+        raise RuntimeError("frosting_b200: ABI version mismatch between header and library")
+    _lib = L
+    return L
+
+
+class Fb200Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().fb200_last_error().decode("utf-8", "replace")
+        raise Fb200Error(f"frosting_b200 error {rc}: {msg}")

@@ -1,0 +1,225 @@
+// api.cu -- the extern "C" boundary declared in include/frosting_b200.h.
+//
+// Mirrors, for this path, what DGR/rasterize_points.cu + CudaRasterizer::Rasterizer do for the
+// reference: argument checks, workspace carving, kernel sequencing.  Differences by design:
+// raw device pointers instead of torch tensors, an explicit stream, no allocation, no host
+// synchronisation unless `debug` is set.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace fb200;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+int check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return FB200_OK;
+    snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return FB200_ECUDA;
+}
+
+// debug mode: synchronise after every stage like CHECK_CUDA (auxiliary.h:166-173)
+int stage(cudaError_t e, const char* what, bool debug, cudaStream_t s) {
+    int rc = check(e, what);
+    if (rc != FB200_OK) return rc;
+    if (debug) return check(cudaStreamSynchronize(s), what);
+    return FB200_OK;
+}
+
+int validate(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws) {
+    if (!prm || !in || !ws) return fail(FB200_EINVAL, "null argument struct%s");
+    if (prm->P < 0 || prm->image_width <= 0 || prm->image_height <= 0)
+        return fail(FB200_EINVAL, "bad extents (P >= 0, image dims > 0 required)%s");
+    if (prm->image_width > 65535 * FB200_TILE || prm->image_height > 65535 * FB200_TILE)
+        return fail(FB200_EINVAL, "image too large for 16-bit tile coordinates%s");
+    if (prm->P > 0) {
+        if (!in->d_means3D || !in->d_opacities) return fail(FB200_EINVAL, "means3D / opacities missing%s");
+        const bool has_sh = in->d_shs != nullptr, has_col = in->d_colors_precomp != nullptr;
+        if (has_sh == has_col)
+            return fail(FB200_EINVAL, "Please provide excatly one of either SHs or precomputed colors!%s");
+        const bool has_sr = in->d_scales != nullptr && in->d_rotations != nullptr;
+        const bool any_sr = in->d_scales != nullptr || in->d_rotations != nullptr;
+        const bool has_cov = in->d_cov3D_precomp != nullptr;
+        if ((!has_sr && !has_cov) || (any_sr && has_cov))
+            return fail(FB200_EINVAL,
+                        "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!%s");
+        if (has_sh && (prm->sh_coeffs <= 0 || prm->sh_degree < 0 || prm->sh_degree > 3 ||
+                       (prm->sh_degree + 1) * (prm->sh_degree + 1) > prm->sh_coeffs))
+            return fail(FB200_EINVAL, "sh_degree / sh_coeffs inconsistent%s");
+    }
+    if (!in->d_background || !in->d_viewmatrix || !in->d_projmatrix || !in->d_campos)
+        return fail(FB200_EINVAL, "camera tensors missing%s");
+    if (!ws->d_geom || !ws->d_image || !ws->d_status) return fail(FB200_EINVAL, "workspace pointers missing%s");
+    if (ws->binning_capacity > 0 && !ws->d_binning) return fail(FB200_EINVAL, "binning buffer missing%s");
+    if (ws->binning_capacity < 0 || ws->binning_capacity > 0x7fffffffLL)
+        return fail(FB200_EINVAL, "binning capacity out of range%s");
+    const GeomLayout gl((size_t)prm->P);
+    const ImageLayout il(prm->image_width, prm->image_height);
+    const BinLayout bl((size_t)ws->binning_capacity);
+    if (ws->geom_bytes < gl.total) return fail(FB200_ENOSPC, "geometry workspace too small%s");
+    if (ws->image_bytes < il.total) return fail(FB200_ENOSPC, "image workspace too small%s");
+    if (ws->binning_bytes < bl.total) return fail(FB200_ENOSPC, "binning workspace too small%s");
+    return FB200_OK;
+}
+
+inline char* align128(void* p) {
+    return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb200_abi_version(void) { return FB200_ABI_VERSION; }
+const char* fb200_last_error(void) { return g_err; }
+
+size_t fb200_geom_bytes(int32_t P) { return GeomLayout((size_t)(P < 0 ? 0 : P)).total; }
+size_t fb200_image_bytes(int32_t W, int32_t H) { return ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
+size_t fb200_binning_bytes(int64_t capacity) { return BinLayout((size_t)(capacity < 0 ? 0 : capacity)).total; }
+
+int fb200_get_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, fb200_layout* out) {
+    if (!out || P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(FB200_EINVAL, "bad layout query%s");
+    const GeomLayout gl((size_t)P);
+    const ImageLayout il(W, H);
+    const BinLayout bl((size_t)capacity);
+    out->geom_rec = gl.rec; out->geom_depth = gl.depth; out->geom_rect = gl.rect; out->geom_clamped = gl.clamped;
+    out->img_final_T = il.final_T; out->img_n_contrib = il.n_contrib; out->img_ranges = il.ranges;
+    out->img_tile_count = il.tile_count;
+    out->bin_point_list = bl.point_list; out->bin_keys = bl.keys;
+    return FB200_OK;
+}
+
+int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                  float* d_out_color, int32_t* d_radii, void* stream) {
+    int rc = validate(prm, in, ws);
+    if (rc != FB200_OK) return rc;
+    if (!d_out_color || (prm->P > 0 && !d_radii)) return fail(FB200_EINVAL, "output pointers missing%s");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool debug = (prm->debug & 1) != 0;
+
+    const GeomLayout gl((size_t)prm->P);
+    const ImageLayout il(prm->image_width, prm->image_height);
+    const BinLayout bl((size_t)ws->binning_capacity);
+    char* g = align128(ws->d_geom);
+    char* im = align128(ws->d_image);
+    char* bn = ws->d_binning ? align128(ws->d_binning) : nullptr;
+
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prm = *prm;
+    a.in = *in;
+    // focal lengths exactly as rasterizer_impl.cu:222-223
+    a.focal_y = prm->image_height / (2.0f * prm->tanfovy);
+    a.focal_x = prm->image_width / (2.0f * prm->tanfovx);
+    a.tiles_x = il.tiles_x; a.tiles_y = il.tiles_y;
+    a.rec = reinterpret_cast<SplatRec*>(g + gl.rec);
+    a.depth = reinterpret_cast<float*>(g + gl.depth);
+    a.rect = reinterpret_cast<uint2*>(g + gl.rect);
+    a.clamped = reinterpret_cast<uint8_t*>(g + gl.clamped);
+    a.final_T = reinterpret_cast<float*>(im + il.final_T);
+    a.n_contrib = reinterpret_cast<uint32_t*>(im + il.n_contrib);
+    a.ranges = reinterpret_cast<uint2*>(im + il.ranges);
+    a.tile_count = reinterpret_cast<uint32_t*>(im + il.tile_count);
+    a.cursor = reinterpret_cast<uint32_t*>(im + il.cursor);
+    a.list_small = reinterpret_cast<uint32_t*>(im + il.list_small);
+    a.list_large = reinterpret_cast<uint32_t*>(im + il.list_large);
+    a.list_huge = reinterpret_cast<uint32_t*>(im + il.list_huge);
+    a.counters = reinterpret_cast<uint32_t*>(im + il.counters);
+    a.point_list = bn ? reinterpret_cast<uint32_t*>(bn + bl.point_list) : nullptr;
+    a.keys = bn ? reinterpret_cast<unsigned long long*>(bn + bl.keys) : nullptr;
+    a.capacity = ws->binning_capacity;
+    a.status = ws->d_status;
+    a.out_color = d_out_color;
+    a.radii = d_radii;
+
+    if ((rc = stage(launch_preprocess_fwd(a, s), "preprocess", debug, s)) != FB200_OK) return rc;
+    if ((rc = stage(launch_binning(a, s), "binning", debug, s)) != FB200_OK) return rc;
+    if ((rc = stage(launch_render_fwd(a, s), "render", debug, s)) != FB200_OK) return rc;
+    return FB200_OK;
+}
+
+int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                   const int32_t* d_radii, const float* d_dL_dout_color, const fb200_grads* grads, void* stream) {
+    int rc = validate(prm, in, ws);
+    if (rc != FB200_OK) return rc;
+    if (!grads || !d_dL_dout_color || (prm->P > 0 && !d_radii)) return fail(FB200_EINVAL, "backward pointers missing%s");
+    if (prm->P > 0 && (!grads->d_dL_dmeans2D || !grads->d_dL_dcolors || !grads->d_dL_dopacity ||
+                       !grads->d_dL_dmeans3D || !grads->d_dL_dcov3D || !grads->d_dL_dscales ||
+                       !grads->d_dL_drotations || (prm->sh_coeffs > 0 && !grads->d_dL_dsh)))
+        return fail(FB200_EINVAL, "gradient output pointers missing%s");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool debug = (prm->debug & 1) != 0;
+    if (prm->P == 0) return FB200_OK;
+
+    const GeomLayout gl((size_t)prm->P);
+    const ImageLayout il(prm->image_width, prm->image_height);
+    const BinLayout bl((size_t)ws->binning_capacity);
+    char* g = align128(ws->d_geom);
+    char* im = align128(ws->d_image);
+    char* bn = ws->d_binning ? align128(ws->d_binning) : nullptr;
+
+    BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prm = *prm;
+    a.in = *in;
+    a.focal_y = prm->image_height / (2.0f * prm->tanfovy);
+    a.focal_x = prm->image_width / (2.0f * prm->tanfovx);
+    a.tiles_x = il.tiles_x; a.tiles_y = il.tiles_y;
+    a.rec = reinterpret_cast<const SplatRec*>(g + gl.rec);
+    a.clamped = reinterpret_cast<const uint8_t*>(g + gl.clamped);
+    a.acc = reinterpret_cast<float*>(g + gl.acc);
+    a.final_T = reinterpret_cast<const float*>(im + il.final_T);
+    a.n_contrib = reinterpret_cast<const uint32_t*>(im + il.n_contrib);
+    a.ranges = reinterpret_cast<const uint2*>(im + il.ranges);
+    a.point_list = bn ? reinterpret_cast<const uint32_t*>(bn + bl.point_list) : nullptr;
+    a.status = ws->d_status;
+    a.radii = d_radii;
+    a.dL_dpix = d_dL_dout_color;
+    a.g = *grads;
+
+    if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc;
+    if ((rc = stage(launch_geom_bwd(a, s), "geometry backward", debug, s)) != FB200_OK) return rc;
+    return FB200_OK;
+}
+
+int fb200_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,
+                       uint8_t* d_present, void* stream) {
+    (void)d_projmatrix;   // the reference's x/y frustum test is commented out (auxiliary.h:154)
+    if (P < 0 || (P > 0 && (!d_means3D || !d_viewmatrix || !d_present)))
+        return fail(FB200_EINVAL, "mark_visible: bad arguments%s");
+    return check(launch_mark_visible(P, d_means3D, d_viewmatrix, d_present, static_cast<cudaStream_t>(stream)),
+                 "mark_visible");
+}
+
+int fb200_mesh_visibility(int32_t V, int32_t F, const float* d_verts, const int32_t* d_faces,
+                          const float* d_full_proj, int32_t W, int32_t H, uint64_t* d_zbuf,
+                          int32_t* d_pix_to_face, uint8_t* d_face_visible, int32_t mark_last_on_bg, void* stream) {
+    if (V < 0 || F < 0 || W <= 0 || H <= 0 || !d_full_proj || !d_zbuf || !d_pix_to_face ||
+        (F > 0 && (!d_verts || !d_faces)))
+        return fail(FB200_EINVAL, "mesh_visibility: bad arguments%s");
+    return check(launch_mesh_visibility(V, F, d_verts, d_faces, d_full_proj, W, H,
+                                        reinterpret_cast<unsigned long long*>(d_zbuf), d_pix_to_face,
+                                        d_face_visible, mark_last_on_bg, static_cast<cudaStream_t>(stream)),
+                 "mesh_visibility");
+}
+
+int fb200_gaussian_mask_from_faces(int32_t n_points, const int64_t* d_point_cell_indices, int32_t F,
+                                   const uint8_t* d_face_visible, int32_t n_background, uint8_t* d_mask,
+                                   void* stream) {
+    if (n_points < 0 || n_background < 0 || F < 0 || (n_points > 0 && (!d_point_cell_indices || !d_face_visible)) ||
+        (n_points + n_background > 0 && !d_mask))
+        return fail(FB200_EINVAL, "gaussian_mask_from_faces: bad arguments%s");
+    return check(launch_mask_from_faces(n_points, reinterpret_cast<const long long*>(d_point_cell_indices), F,
+                                        d_face_visible, n_background, d_mask, static_cast<cudaStream_t>(stream)),
+                 "gaussian_mask_from_faces");
+}
+
+}  // extern "C"

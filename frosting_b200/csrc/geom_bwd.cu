@@ -1,0 +1,280 @@
+// geom_bwd.cu -- per-Gaussian backward: conic -> cov2D -> (cov3D, mean), projected mean -> mean,
+// colour -> SH (+ view direction -> mean), cov3D -> scale / quaternion.
+//
+// One fused kernel replaces computeCov2DCUDA (DGR/cuda_rasterizer/backward.cu:144-274) and
+// preprocessCUDA backward (backward.cu:346-396 with computeColorFromSH backward :20-139 and
+// computeCov3D backward :278-341), and removes the nine zero-filled gradient tensors of
+// DGR/rasterize_points.cu:151-159: every output element is written exactly once here (zeros for
+// Gaussians with radii == 0), so the caller allocates with torch.empty.
+//
+// Gradients are tolerance-level quantities (the reference accumulates them with unordered float
+// atomics), so this file is written in plain C++ from the maths, not from the reference's op order:
+//   cov2D = M S M^T with M = J * W (2x3),  conic = cov2D^-1,
+//   S = R^T diag(s)^2 R,  colour = clamp(sum_k b_k(dir) sh_k + 0.5).
+// Quirks of the reference that ARE reproduced because they change the values:
+//   * d(scale) omits the chain factor scale_modifier (backward.cu:318-321),
+//   * the quaternion gradient is w.r.t. the un-normalised input (backward.cu:340),
+//   * denom2inv = 1 / (det^2 + 1e-7) (backward.cu:203) and its == 0 guard,
+//   * the 1.3*tanfov clamp masks on d/dt.x, d/dt.y (backward.cu:175-176).
+#include "common.cuh"
+
+namespace fb200 {
+
+namespace {
+
+__device__ constexpr float kC0 = 0.28209479177387814f;
+__device__ constexpr float kC1 = 0.4886025119029199f;
+__device__ constexpr float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                     -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                     0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                     -0.5900435899266435f};
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// symmetric 3x3 times vector, S = (c0 c1 c2; c1 c3 c4; c2 c4 c5)
+__device__ __forceinline__ V3 symv(const float* c, V3 t) {
+    return v3(c[0] * t.x + c[1] * t.y + c[2] * t.z,
+              c[1] * t.x + c[3] * t.y + c[4] * t.z,
+              c[2] * t.x + c[4] * t.y + c[5] * t.z);
+}
+
+__global__ void __launch_bounds__(256)
+geom_bwd_kernel(BwdArgs a) {
+    __shared__ float view[16], proj[16], campos[3];
+    if (threadIdx.x < 16) {
+        view[threadIdx.x] = a.in.d_viewmatrix[threadIdx.x];
+        proj[threadIdx.x] = a.in.d_projmatrix[threadIdx.x];
+    }
+    if (threadIdx.x < 3) campos[threadIdx.x] = a.in.d_campos[threadIdx.x];
+    __syncthreads();
+
+    const int P = a.prm.P, M = a.prm.sh_coeffs, D = a.prm.sh_degree;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const size_t i = (size_t)idx;
+
+    const bool visible = a.radii[idx] > 0;
+
+    float g_mean2d_x = 0.f, g_mean2d_y = 0.f, g_op = 0.f;
+    V3 g_col = v3(0.f, 0.f, 0.f), g_mean = v3(0.f, 0.f, 0.f);
+    float g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    V3 g_scale = v3(0.f, 0.f, 0.f);
+    float4 g_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const bool has_sh = a.in.d_shs != nullptr && M > 0;
+    float* dsh = (a.g.d_dL_dsh != nullptr && M > 0) ? a.g.d_dL_dsh + i * M * 3 : nullptr;
+
+    if (visible) {
+        const float4* accp = reinterpret_cast<const float4*>(a.acc + i * 12);
+        const float4 a0 = accp[0], a1 = accp[1];
+        const float a2x = a.acc[i * 12 + 8];
+        g_mean2d_x = a0.x; g_mean2d_y = a0.y;
+        const float dLc_x = a0.z, dLc_y = a0.w, dLc_w = a1.x;   // dL/dconic (x, y, w)
+        g_op = a1.y;
+        g_col = v3(a1.z, a1.w, a2x);
+
+        const float mx = a.in.d_means3D[3 * i], my = a.in.d_means3D[3 * i + 1], mz = a.in.d_means3D[3 * i + 2];
+
+        // ---- 3D covariance (recomputed from scale/rotation, or the precomputed input) ----
+        float S[6];
+        float sx = 0.f, sy = 0.f, sz = 0.f, qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        float Rm[3][3];   // Rm[row][col], maths convention: Sigma = Rm^T diag(s)^2 Rm
+        const bool from_sr = a.in.d_cov3D_precomp == nullptr;
+        if (from_sr) {
+            const float mod = a.prm.scale_modifier;
+            sx = mod * a.in.d_scales[3 * i]; sy = mod * a.in.d_scales[3 * i + 1]; sz = mod * a.in.d_scales[3 * i + 2];
+            const float4 q = reinterpret_cast<const float4*>(a.in.d_rotations)[i];
+            qr = q.x; qx = q.y; qy = q.z; qz = q.w;
+            Rm[0][0] = 1.f - 2.f * (qy * qy + qz * qz); Rm[0][1] = 2.f * (qx * qy + qr * qz); Rm[0][2] = 2.f * (qx * qz - qr * qy);
+            Rm[1][0] = 2.f * (qx * qy - qr * qz); Rm[1][1] = 1.f - 2.f * (qx * qx + qz * qz); Rm[1][2] = 2.f * (qy * qz + qr * qx);
+            Rm[2][0] = 2.f * (qx * qz + qr * qy); Rm[2][1] = 2.f * (qy * qz - qr * qx); Rm[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+            const float s2[3] = {sx * sx, sy * sy, sz * sz};
+            int k = 0;
+            for (int r = 0; r < 3; ++r)
+                for (int c = r; c < 3; ++c, ++k)
+                    S[k] = s2[0] * Rm[0][r] * Rm[0][c] + s2[1] * Rm[1][r] * Rm[1][c] + s2[2] * Rm[2][r] * Rm[2][c];
+        } else {
+            for (int k = 0; k < 6; ++k) S[k] = a.in.d_cov3D_precomp[6 * i + k];
+        }
+
+        // ---- conic -> cov2D -> cov3D and view-space mean ----
+        const float tx_raw = view[0] * mx + view[4] * my + view[8] * mz + view[12];
+        const float ty_raw = view[1] * mx + view[5] * my + view[9] * mz + view[13];
+        const float tz = view[2] * mx + view[6] * my + view[10] * mz + view[14];
+        const float limx = 1.3f * a.prm.tanfovx, limy = 1.3f * a.prm.tanfovy;
+        const float txtz = tx_raw / tz, tytz = ty_raw / tz;
+        const float tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+        const float ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+        const float fx = a.focal_x, fy = a.focal_y;
+        const float J00 = fx / tz, J02 = -(fx * tx) / (tz * tz), J11 = fy / tz, J12 = -(fy * ty) / (tz * tz);
+        // rows of M = J * W, W[i][j] = view[4*j + i]
+        const V3 T0 = v3(J00 * view[0] + J02 * view[2], J00 * view[4] + J02 * view[6], J00 * view[8] + J02 * view[10]);
+        const V3 T1 = v3(J11 * view[1] + J12 * view[2], J11 * view[5] + J12 * view[6], J11 * view[9] + J12 * view[10]);
+        const V3 ST0 = symv(S, T0), ST1 = symv(S, T1);
+        const float ca = dot(T0, ST0) + 0.3f, cb = dot(T0, ST1), cc = dot(T1, ST1) + 0.3f;
+        const float denom = ca * cc - cb * cb;
+        const float denom2inv = 1.0f / (denom * denom + 0.0000001f);
+        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+        if (denom2inv != 0.f) {
+            dL_da = denom2inv * (-cc * cc * dLc_x + 2.f * cb * cc * dLc_y + (denom - ca * cc) * dLc_w);
+            dL_dc = denom2inv * (-ca * ca * dLc_w + 2.f * ca * cb * dLc_y + (denom - ca * cc) * dLc_x);
+            dL_db = denom2inv * 2.f * (cb * cc * dLc_x - (denom + 2.f * cb * cb) * dLc_y + ca * cb * dLc_w);
+            // d cov2D / d Sigma (off-diagonals appear twice)
+            g_cov[0] = T0.x * T0.x * dL_da + T0.x * T1.x * dL_db + T1.x * T1.x * dL_dc;
+            g_cov[3] = T0.y * T0.y * dL_da + T0.y * T1.y * dL_db + T1.y * T1.y * dL_dc;
+            g_cov[5] = T0.z * T0.z * dL_da + T0.z * T1.z * dL_db + T1.z * T1.z * dL_dc;
+            g_cov[1] = 2.f * T0.x * T0.y * dL_da + (T0.x * T1.y + T0.y * T1.x) * dL_db + 2.f * T1.x * T1.y * dL_dc;
+            g_cov[2] = 2.f * T0.x * T0.z * dL_da + (T0.x * T1.z + T0.z * T1.x) * dL_db + 2.f * T1.x * T1.z * dL_dc;
+            g_cov[4] = 2.f * T0.z * T0.y * dL_da + (T0.y * T1.z + T0.z * T1.y) * dL_db + 2.f * T1.y * T1.z * dL_dc;
+        }
+        // d/dT rows, then d/dJ, then d/dt
+        const V3 dT0 = v3(2.f * ST0.x * dL_da + ST1.x * dL_db, 2.f * ST0.y * dL_da + ST1.y * dL_db, 2.f * ST0.z * dL_da + ST1.z * dL_db);
+        const V3 dT1 = v3(2.f * ST1.x * dL_dc + ST0.x * dL_db, 2.f * ST1.y * dL_dc + ST0.y * dL_db, 2.f * ST1.z * dL_dc + ST0.z * dL_db);
+        const float dJ00 = view[0] * dT0.x + view[4] * dT0.y + view[8] * dT0.z;
+        const float dJ02 = view[2] * dT0.x + view[6] * dT0.y + view[10] * dT0.z;
+        const float dJ11 = view[1] * dT1.x + view[5] * dT1.y + view[9] * dT1.z;
+        const float dJ12 = view[2] * dT1.x + view[6] * dT1.y + view[10] * dT1.z;
+        const float itz = 1.f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+        const float dtx = x_grad_mul * -fx * itz2 * dJ02;
+        const float dty = y_grad_mul * -fy * itz2 * dJ12;
+        const float dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2.f * fx * tx) * itz3 * dJ02 + (2.f * fy * ty) * itz3 * dJ12;
+        g_mean = v3(view[0] * dtx + view[1] * dty + view[2] * dtz,
+                    view[4] * dtx + view[5] * dty + view[6] * dtz,
+                    view[8] * dtx + view[9] * dty + view[10] * dtz);
+
+        // ---- projected mean -> mean ----
+        {
+            const float hx = proj[0] * mx + proj[4] * my + proj[8] * mz + proj[12];
+            const float hy = proj[1] * mx + proj[5] * my + proj[9] * mz + proj[13];
+            const float hw = proj[3] * mx + proj[7] * my + proj[11] * mz + proj[15];
+            const float m_w = 1.0f / (hw + 0.0000001f);
+            const float mul1 = hx * m_w * m_w, mul2 = hy * m_w * m_w;
+            g_mean.x += (proj[0] * m_w - proj[3] * mul1) * g_mean2d_x + (proj[1] * m_w - proj[3] * mul2) * g_mean2d_y;
+            g_mean.y += (proj[4] * m_w - proj[7] * mul1) * g_mean2d_x + (proj[5] * m_w - proj[7] * mul2) * g_mean2d_y;
+            g_mean.z += (proj[8] * m_w - proj[11] * mul1) * g_mean2d_x + (proj[9] * m_w - proj[11] * mul2) * g_mean2d_y;
+        }
+
+        // ---- colour -> SH coefficients and view direction ----
+        if (has_sh) {
+            const uint8_t cl = a.clamped[idx];
+            const V3 dRGB = v3((cl & 1) ? 0.f : g_col.x, (cl & 2) ? 0.f : g_col.y, (cl & 4) ? 0.f : g_col.z);
+            const V3 dorig = v3(mx - campos[0], my - campos[1], mz - campos[2]);
+            const float len = sqrtf(dot(dorig, dorig));
+            const float x = dorig.x / len, y = dorig.y / len, z = dorig.z / len;
+            const float* sh = a.in.d_shs + i * M * 3;
+            // basis value and gradient per coefficient
+            float bv[16], bx[16], by[16], bz[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { bv[k] = 0.f; bx[k] = 0.f; by[k] = 0.f; bz[k] = 0.f; }
+            bv[0] = kC0;
+            if (D > 0) {
+                bv[1] = -kC1 * y; by[1] = -kC1;
+                bv[2] = kC1 * z;  bz[2] = kC1;
+                bv[3] = -kC1 * x; bx[3] = -kC1;
+                if (D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    bv[4] = kC2[0] * xy;                 bx[4] = kC2[0] * y;        by[4] = kC2[0] * x;
+                    bv[5] = kC2[1] * yz;                 by[5] = kC2[1] * z;        bz[5] = kC2[1] * y;
+                    bv[6] = kC2[2] * (2.f * zz - xx - yy); bx[6] = kC2[2] * 2.f * -x; by[6] = kC2[2] * 2.f * -y; bz[6] = kC2[2] * 4.f * z;
+                    bv[7] = kC2[3] * xz;                 bx[7] = kC2[3] * z;        bz[7] = kC2[3] * x;
+                    bv[8] = kC2[4] * (xx - yy);          bx[8] = kC2[4] * 2.f * x;  by[8] = kC2[4] * 2.f * -y;
+                    if (D > 2) {
+                        bv[9] = kC3[0] * y * (3.f * xx - yy);            bx[9] = kC3[0] * 6.f * xy;  by[9] = kC3[0] * 3.f * (xx - yy);
+                        bv[10] = kC3[1] * xy * z;                        bx[10] = kC3[1] * yz;      by[10] = kC3[1] * xz;   bz[10] = kC3[1] * xy;
+                        bv[11] = kC3[2] * y * (4.f * zz - xx - yy);      bx[11] = kC3[2] * -2.f * xy; by[11] = kC3[2] * (-3.f * yy + 4.f * zz - xx); bz[11] = kC3[2] * 8.f * yz;
+                        bv[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); bx[12] = kC3[3] * -6.f * xz; by[12] = kC3[3] * -6.f * yz; bz[12] = kC3[3] * 3.f * (2.f * zz - xx - yy);
+                        bv[13] = kC3[4] * x * (4.f * zz - xx - yy);      bx[13] = kC3[4] * (-3.f * xx + 4.f * zz - yy); by[13] = kC3[4] * -2.f * xy; bz[13] = kC3[4] * 8.f * xz;
+                        bv[14] = kC3[5] * z * (xx - yy);                 bx[14] = kC3[5] * 2.f * xz; by[14] = kC3[5] * -2.f * yz; bz[14] = kC3[5] * (xx - yy);
+                        bv[15] = kC3[6] * x * (xx - 3.f * yy);           bx[15] = kC3[6] * 3.f * (xx - yy); by[15] = kC3[6] * -6.f * xy;
+                    }
+                }
+            }
+            const int ncoef = (D + 1) * (D + 1);
+            V3 dcdx = v3(0.f, 0.f, 0.f), dcdy = v3(0.f, 0.f, 0.f), dcdz = v3(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < M) {
+                    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+                    if (k < ncoef) {
+                        o0 = bv[k] * dRGB.x; o1 = bv[k] * dRGB.y; o2 = bv[k] * dRGB.z;
+                        if (k > 0) {
+                            const float s0 = sh[3 * k], s1 = sh[3 * k + 1], s2 = sh[3 * k + 2];
+                            dcdx.x += bx[k] * s0; dcdx.y += bx[k] * s1; dcdx.z += bx[k] * s2;
+                            dcdy.x += by[k] * s0; dcdy.y += by[k] * s1; dcdy.z += by[k] * s2;
+                            dcdz.x += bz[k] * s0; dcdz.y += bz[k] * s1; dcdz.z += bz[k] * s2;
+                        }
+                    }
+                    dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
+                }
+            }
+            for (int k = 16; k < M; ++k) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+            // through dir = dorig / |dorig|:  d/dv = (dv |v|^2 - v (v . dv)) / |v|^3
+            const V3 ddir = v3(dot(dcdx, dRGB), dot(dcdy, dRGB), dot(dcdz, dRGB));
+            const float sum2 = dot(dorig, dorig);
+            const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            const float vd = dot(dorig, ddir);
+            g_mean.x += (ddir.x * sum2 - dorig.x * vd) * inv32;
+            g_mean.y += (ddir.y * sum2 - dorig.y * vd) * inv32;
+            g_mean.z += (ddir.z * sum2 - dorig.z * vd) * inv32;
+        }
+
+        // ---- cov3D -> scale, quaternion ----
+        if (from_sr) {
+            // dL/dSigma as a symmetric matrix (off-diagonals halved), dL/dMm = 2 * Mm * dL/dSigma,
+            // Mm[r][c] = s_r * Rm[r][c]
+            const float dS[3][3] = {{g_cov[0], 0.5f * g_cov[1], 0.5f * g_cov[2]},
+                                    {0.5f * g_cov[1], g_cov[3], 0.5f * g_cov[4]},
+                                    {0.5f * g_cov[2], 0.5f * g_cov[4], g_cov[5]}};
+            const float sv[3] = {sx, sy, sz};
+            float Gm[3][3];   // dL/dRm[r][c] = s_r * dL/dMm[r][c]
+            float gs[3];
+            for (int r = 0; r < 3; ++r) {
+                float acc_s = 0.f;
+                for (int c = 0; c < 3; ++c) {
+                    const float dMm = 2.f * sv[r] * (Rm[r][0] * dS[0][c] + Rm[r][1] * dS[1][c] + Rm[r][2] * dS[2][c]);
+                    acc_s += Rm[r][c] * dMm;
+                    Gm[r][c] = sv[r] * dMm;
+                }
+                gs[r] = acc_s;
+            }
+            g_scale = v3(gs[0], gs[1], gs[2]);
+            // Rm[0][1] = 2(xy+rz), Rm[0][2] = 2(xz-ry), Rm[1][0] = 2(xy-rz), Rm[1][2] = 2(yz+rx),
+            // Rm[2][0] = 2(xz+ry), Rm[2][1] = 2(yz-rx); the reference indexes dL_dMt[a][b] with
+            // a = row of its S (our r) and b = column index of glm R^T ... expressed here directly:
+            // H[a][b] := dL/d(R_glm[b][a]) where R_glm[b][a] = Rm[a][b]^T convention of backward.cu:296-300
+            // -> H[a][b] = Gm[a][b] with Rm_ref(a,b) = R_glm[b][a].  R_glm[col][row]: col0 = (1-2(yy+zz), 2(xy-rz), 2(xz+ry))
+            // so Rm_ref(0,1) = R_glm[1][0] = 2(xy+rz) = Rm[0][1].  Identical indexing.
+            const float (&Hm)[3][3] = Gm;
+            g_rot.x = 2.f * qz * (Hm[0][1] - Hm[1][0]) + 2.f * qy * (Hm[2][0] - Hm[0][2]) + 2.f * qx * (Hm[1][2] - Hm[2][1]);
+            g_rot.y = 2.f * qy * (Hm[1][0] + Hm[0][1]) + 2.f * qz * (Hm[2][0] + Hm[0][2]) + 2.f * qr * (Hm[1][2] - Hm[2][1]) - 4.f * qx * (Hm[2][2] + Hm[1][1]);
+            g_rot.z = 2.f * qx * (Hm[1][0] + Hm[0][1]) + 2.f * qr * (Hm[2][0] - Hm[0][2]) + 2.f * qz * (Hm[1][2] + Hm[2][1]) - 4.f * qy * (Hm[2][2] + Hm[0][0]);
+            g_rot.w = 2.f * qr * (Hm[0][1] - Hm[1][0]) + 2.f * qx * (Hm[2][0] + Hm[0][2]) + 2.f * qy * (Hm[1][2] + Hm[2][1]) - 4.f * qz * (Hm[1][1] + Hm[0][0]);
+        }
+    } else if (dsh != nullptr) {
+        for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
+    }
+    if (visible && !has_sh && dsh != nullptr)
+        for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
+
+    a.g.d_dL_dmeans2D[3 * i] = g_mean2d_x; a.g.d_dL_dmeans2D[3 * i + 1] = g_mean2d_y; a.g.d_dL_dmeans2D[3 * i + 2] = 0.f;
+    a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z;
+    a.g.d_dL_dopacity[i] = g_op;
+    a.g.d_dL_dmeans3D[3 * i] = g_mean.x; a.g.d_dL_dmeans3D[3 * i + 1] = g_mean.y; a.g.d_dL_dmeans3D[3 * i + 2] = g_mean.z;
+    for (int k = 0; k < 6; ++k) a.g.d_dL_dcov3D[6 * i + k] = g_cov[k];
+    a.g.d_dL_dscales[3 * i] = g_scale.x; a.g.d_dL_dscales[3 * i + 1] = g_scale.y; a.g.d_dL_dscales[3 * i + 2] = g_scale.z;
+    reinterpret_cast<float4*>(a.g.d_dL_drotations)[i] = g_rot;
+}
+
+}  // namespace
+
+cudaError_t launch_geom_bwd(const BwdArgs& a, cudaStream_t s) {
+    if (a.prm.P > 0) geom_bwd_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace fb200

@@ -1,0 +1,233 @@
+// mesh_vis.cu -- occlusion-culling prepass: which base-mesh faces own at least one pixel.
+//
+// Replaces the OpenGL hardware rasterisation behind nvdiffrast's dr.rasterize as Frosting uses it
+// (frosting_utils/nvdiffrast.py:42-54, frosting_utils/mesh_rasterization.py:121-148):
+//   clip = [v, 1] @ full_proj_transform;  GL clip volume -w <= z <= w;  pixel-centre sampling with a
+//   top-left fill rule;  nearest depth wins (ties: lowest face id, i.e. first drawn under GL_LESS);
+//   output face id per pixel (-1 = background), no back-face culling.
+// On the hot path only the SET of visible faces is consumed (frosting_model.py:1534-1539,
+// frosting_trainers/refine.py:436-441).
+//
+// Design: the shell base has ~1-2 M triangles at 1080p, i.e. most triangles cover a pixel or two, so
+// the rasteriser is a per-triangle scan with a 64-bit atomicMin z-buffer (depth_bits<<32 | face):
+// one thread per small triangle, one warp / one CTA per larger one (size-classed by bounding box,
+// three launches of the same kernel), followed by a resolve pass.  No binning is needed at this
+// triangle size and the z-buffer (16.6 MB at 1080p) lives in L2.
+#include "common.cuh"
+
+namespace fb200 {
+
+namespace {
+
+typedef unsigned long long u64;
+
+struct ClipV { float x, y, z, w; };
+
+__device__ __forceinline__ ClipV to_clip(const float* __restrict__ m, float x, float y, float z) {
+    ClipV c;
+    c.x = m[0] * x + m[4] * y + m[8] * z + m[12];
+    c.y = m[1] * x + m[5] * y + m[9] * z + m[13];
+    c.z = m[2] * x + m[6] * y + m[10] * z + m[14];
+    c.w = m[3] * x + m[7] * y + m[11] * z + m[15];
+    return c;
+}
+
+__device__ __forceinline__ ClipV lerp(const ClipV& a, const ClipV& b, float t) {
+    ClipV c;
+    c.x = a.x + (b.x - a.x) * t; c.y = a.y + (b.y - a.y) * t;
+    c.z = a.z + (b.z - a.z) * t; c.w = a.w + (b.w - a.w) * t;
+    return c;
+}
+
+struct ScreenV { float x, y, z; };   // window coordinates (pixel centres at +0.5), depth in [0,1]
+
+// Edge function with canonical endpoint order so that the two triangles sharing an edge see exactly
+// opposite values (watertight, no double hits).
+__device__ __forceinline__ float edge_fn(const ScreenV& a, const ScreenV& b, float px, float py) {
+    const bool swap = (a.x > b.x) || (a.x == b.x && a.y > b.y);
+    const ScreenV& p = swap ? b : a;
+    const ScreenV& q = swap ? a : b;
+    const float e = (q.x - p.x) * (py - p.y) - (q.y - p.y) * (px - p.x);
+    return swap ? -e : e;
+}
+
+// Top-left ownership of an edge a->b of a triangle normalised to positive edge_fn area (row index
+// grows with y): a horizontal edge with the interior at larger y has dx > 0 ("top"), an edge with
+// the interior at larger x has dy < 0 ("left").  A shared edge is traversed in opposite directions by
+// its two triangles, so exactly one of them owns the pixels lying exactly on it.
+__device__ __forceinline__ bool is_top_left(const ScreenV& a, const ScreenV& b) {
+    const float dx = b.x - a.x, dy = b.y - a.y;
+    return (dy == 0.f && dx > 0.f) || (dy < 0.f);
+}
+
+template <int kGroup>
+__device__ void raster_triangle(ScreenV v0, ScreenV v1, ScreenV v2, int W, int H, int face, int lane,
+                                int area_lo, int area_hi, u64* __restrict__ zbuf) {
+    float area = edge_fn(v0, v1, v2.x, v2.y);
+    if (area == 0.f || !(area == area)) return;
+    if (area < 0.f) {   // make orientation positive
+        ScreenV t = v1; v1 = v2; v2 = t;
+        area = -area;
+    }
+    const float minx = fminf(v0.x, fminf(v1.x, v2.x)), maxx = fmaxf(v0.x, fmaxf(v1.x, v2.x));
+    const float miny = fminf(v0.y, fminf(v1.y, v2.y)), maxy = fmaxf(v0.y, fmaxf(v1.y, v2.y));
+    // pixels whose centre (i+0.5) can lie inside [min, max]
+    int x0 = max(0, (int)ceilf(minx - 0.5f)), x1 = min(W - 1, (int)floorf(maxx - 0.5f));
+    int y0 = max(0, (int)ceilf(miny - 0.5f)), y1 = min(H - 1, (int)floorf(maxy - 0.5f));
+    if (x0 > x1 || y0 > y1) return;
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const long long barea = (long long)bw * bh;
+    if (barea <= area_lo || barea > area_hi) return;
+    const bool tl0 = is_top_left(v1, v2), tl1 = is_top_left(v2, v0), tl2 = is_top_left(v0, v1);
+    const float inv_area = 1.0f / area;
+    for (long long k = lane; k < barea; k += kGroup) {
+        const int px = x0 + (int)(k % bw), py = y0 + (int)(k / bw);
+        const float cx = px + 0.5f, cy = py + 0.5f;
+        const float w0 = edge_fn(v1, v2, cx, cy);
+        const float w1 = edge_fn(v2, v0, cx, cy);
+        const float w2 = edge_fn(v0, v1, cx, cy);
+        const bool in0 = w0 > 0.f || (w0 == 0.f && tl0);
+        const bool in1 = w1 > 0.f || (w1 == 0.f && tl1);
+        const bool in2 = w2 > 0.f || (w2 == 0.f && tl2);
+        if (!(in0 && in1 && in2)) continue;
+        const float z = (w0 * v0.z + w1 * v1.z + w2 * v2.z) * inv_area;
+        if (!(z >= 0.f && z <= 1.f)) continue;   // per-fragment near/far clip (-w <= z_clip <= w)
+        const u64 key = ((u64)__float_as_uint(z) << 32) | (uint32_t)face;
+        atomicMin(zbuf + (size_t)py * W + px, key);
+    }
+}
+
+__device__ __forceinline__ ScreenV to_screen(const ClipV& c, int W, int H) {
+    const float iw = 1.0f / c.w;
+    ScreenV s;
+    s.x = (c.x * iw * 0.5f + 0.5f) * W;
+    s.y = (c.y * iw * 0.5f + 0.5f) * H;
+    s.z = c.z * iw * 0.5f + 0.5f;
+    return s;
+}
+
+template <int kGroup>
+__global__ void __launch_bounds__(256)
+raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                    const float* __restrict__ proj, int W, int H, int area_lo, int area_hi,
+                    u64* __restrict__ zbuf) {
+    __shared__ float m[16];
+    if (threadIdx.x < 16) m[threadIdx.x] = proj[threadIdx.x];
+    __syncthreads();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = gtid / kGroup;
+    const int lane = (int)(gtid % kGroup);
+    if (f >= F) return;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    ClipV c[3];
+    c[0] = to_clip(m, verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]);
+    c[1] = to_clip(m, verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
+    c[2] = to_clip(m, verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]);
+    // near plane of the GL clip volume: z + w >= 0 (implies w > 0 for any sane projection)
+    const float d0 = c[0].z + c[0].w, d1 = c[1].z + c[1].w, d2 = c[2].z + c[2].w;
+    const bool in0 = d0 >= 0.f && c[0].w > 1e-12f, in1 = d1 >= 0.f && c[1].w > 1e-12f, in2 = d2 >= 0.f && c[2].w > 1e-12f;
+    const int nin = (int)in0 + (int)in1 + (int)in2;
+    if (nin == 0) return;
+    if (nin == 3) {
+        raster_triangle<kGroup>(to_screen(c[0], W, H), to_screen(c[1], W, H), to_screen(c[2], W, H), W, H,
+                                (int)f, lane, area_lo, area_hi, zbuf);
+        return;
+    }
+    // Sutherland-Hodgman against the near plane: up to 4 vertices
+    ClipV poly[4];
+    int np = 0;
+    const float d[3] = {d0, d1, d2};
+    const bool in[3] = {in0, in1, in2};
+    for (int e = 0; e < 3; ++e) {
+        const int a = e, b = (e + 1) % 3;
+        if (in[a]) poly[np++] = c[a];
+        if (in[a] != in[b]) {
+            const float t = d[a] / (d[a] - d[b]);
+            ClipV p = lerp(c[a], c[b], t);
+            if (!(p.w > 1e-12f)) p.w = 1e-12f;
+            poly[np++] = p;
+        }
+    }
+    if (np < 3) return;
+    ScreenV s0 = to_screen(poly[0], W, H), s1 = to_screen(poly[1], W, H), s2 = to_screen(poly[2], W, H);
+    raster_triangle<kGroup>(s0, s1, s2, W, H, (int)f, lane, area_lo, area_hi, zbuf);
+    if (np == 4) {
+        ScreenV s3 = to_screen(poly[3], W, H);
+        raster_triangle<kGroup>(s0, s2, s3, W, H, (int)f, lane, area_lo, area_hi, zbuf);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+resolve_kernel(int N, int F, const u64* __restrict__ zbuf, int32_t* __restrict__ pix_to_face,
+               uint8_t* __restrict__ face_visible, int mark_last_on_bg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const u64 k = zbuf[i];
+    int face = -1;
+    if (k != ~0ull) face = (int)(uint32_t)k;
+    pix_to_face[i] = face;
+    if (face_visible != nullptr) {
+        if (face >= 0) face_visible[face] = 1;
+        else if (mark_last_on_bg && F > 0) face_visible[F - 1] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mask_from_faces_kernel(int n_points, const long long* __restrict__ cells, int F,
+                       const uint8_t* __restrict__ face_visible, int n_bg, uint8_t* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points + n_bg) return;
+    if (i < n_points) {
+        long long c = cells[i];
+        if (c < 0) c += F;   // torch negative indexing
+        mask[i] = (c >= 0 && c < F) ? face_visible[c] : 0;
+    } else {
+        mask[i] = 1;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_mesh_visibility(int V, int F, const float* verts, const int32_t* faces, const float* proj,
+                                   int W, int H, unsigned long long* zbuf, int32_t* pix_to_face,
+                                   uint8_t* face_visible, int mark_last_on_bg, cudaStream_t s) {
+    (void)V;
+    const size_t N = (size_t)W * H;
+    cudaError_t e = cudaMemsetAsync(zbuf, 0xff, N * 8, s);
+    if (e != cudaSuccess) return e;
+    if (face_visible != nullptr && F > 0) {
+        e = cudaMemsetAsync(face_visible, 0, (size_t)F, s);
+        if (e != cudaSuccess) return e;
+    }
+    if (F > 0) {
+        const int kSmall = 32, kMid = 8192;
+        {
+            const long long threads = (long long)F;
+            raster_faces_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+                F, verts, faces, proj, W, H, 0, kSmall, zbuf);
+        }
+        {
+            const long long threads = (long long)F * 32;
+            raster_faces_kernel<32><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+                F, verts, faces, proj, W, H, kSmall, kMid, zbuf);
+        }
+        {
+            const long long threads = (long long)F * 256;
+            raster_faces_kernel<256><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+                F, verts, faces, proj, W, H, kMid, 0x7fffffff, zbuf);
+        }
+    }
+    if (N > 0)
+        resolve_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>((int)N, F, zbuf, pix_to_face, face_visible,
+                                                                   mark_last_on_bg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask_from_faces(int n_points, const long long* cells, int F, const uint8_t* face_visible,
+                                   int n_bg, uint8_t* mask, cudaStream_t s) {
+    const int n = n_points + n_bg;
+    if (n > 0) mask_from_faces_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_points, cells, F, face_visible, n_bg, mask);
+    return cudaGetLastError();
+}
+
+}  // namespace fb200

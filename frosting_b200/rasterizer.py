@@ -1,0 +1,327 @@
+"""Python surface of the B200 rasterizer -- a drop-in for `diff_gaussian_rasterization`.
+
+Mirrors DGR/diff_gaussian_rasterization/__init__.py (DGR = gaussian_splatting/submodules/
+diff-gaussian-rasterization in the reference):
+  GaussianRasterizationSettings  <- __init__.py:157-169 (same 12 fields, same order)
+  GaussianRasterizer             <- __init__.py:171-220 (same forward signature, same exceptions,
+                                    same (color[3,H,W], radii[P]) return, markVisible)
+  _RasterizeGaussians            <- __init__.py:44-155  (same 8 gradients in the same order)
+The native side is reached through the C ABI in include/frosting_b200.h via ctypes; torch only owns
+the tensors and the stream.
+
+One extension: `GaussianRasterizer.forward(..., visibility_mask=None)` takes the per-Gaussian
+occlusion mask (frosting_model.py:1564-1576) and drops masked Gaussians inside the preprocess kernel
+instead of boolean-gathering every attribute tensor (frosting_model.py:1578-1586).
+"""
+from typing import NamedTuple, Optional
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import Params, Inputs, Workspace, Grads, Layout
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# instance-capacity hint per device: the binning buffer is sized optimistically from the previous
+# frame and the forward is re-run if the device-side overflow flag comes back set (the reference
+# instead stalls the pipeline on a D2H copy between preprocess and binning).
+_capacity_hint = {}
+NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove it is output-neutral
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None or t.numel() == 0:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, device, name: str) -> torch.Tensor:
+    if t.numel() == 0:
+        return t
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous()
+
+
+class _Call:
+    """Everything one forward needs again in backward (kept alive by the autograd ctx)."""
+    __slots__ = ("prm", "inp", "ws", "tensors", "geom", "image", "binning", "status", "capacity",
+                 "num_rendered", "device")
+
+
+def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                    rs: GaussianRasterizationSettings, visibility):
+    L = _lib.lib()
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:57-59
+    if not means3D.is_cuda:
+        raise RuntimeError("frosting_b200 runs on CUDA tensors only (no CPU fallback)")
+    device = means3D.device
+    P = means3D.size(0)
+    H, W = int(rs.image_height), int(rs.image_width)
+
+    means3D = _f32c(means3D, device, "means3D")
+    sh = _f32c(sh, device, "shs")
+    colors_precomp = _f32c(colors_precomp, device, "colors_precomp")
+    opacities = _f32c(opacities, device, "opacities")
+    scales = _f32c(scales, device, "scales")
+    rotations = _f32c(rotations, device, "rotations")
+    cov3Ds_precomp = _f32c(cov3Ds_precomp, device, "cov3D_precomp")
+    bg = _f32c(rs.bg, device, "bg")
+    view = _f32c(rs.viewmatrix, device, "viewmatrix")
+    proj = _f32c(rs.projmatrix, device, "projmatrix")
+    campos = _f32c(rs.campos, device, "campos")
+    vis = None
+    if visibility is not None:
+        vis = visibility.to(device=device, dtype=torch.uint8).contiguous() if visibility.dtype != torch.uint8 \
+            else visibility.to(device).contiguous()
+        if vis.numel() != P:
+            raise RuntimeError("visibility_mask must have one entry per Gaussian")
+
+    M = sh.size(1) if sh.numel() != 0 else 0   # rasterize_points.cu:84-87
+
+    prm = Params(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=int(M), image_width=W, image_height=H,
+                 tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
+                 scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
+                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0))
+    inp = Inputs(d_background=_ptr(bg), d_means3D=_ptr(means3D), d_shs=_ptr(sh),
+                 d_colors_precomp=_ptr(colors_precomp), d_opacities=_ptr(opacities), d_scales=_ptr(scales),
+                 d_rotations=_ptr(rotations), d_cov3D_precomp=_ptr(cov3Ds_precomp),
+                 d_viewmatrix=_ptr(view), d_projmatrix=_ptr(proj), d_campos=_ptr(campos), d_visibility=_ptr(vis))
+
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device)
+        out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        geom = torch.empty((L.fb200_geom_bytes(P),), dtype=torch.uint8, device=device)
+        image = torch.empty((L.fb200_image_bytes(W, H),), dtype=torch.uint8, device=device)
+        status = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, device=device)
+        status_host = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, pin_memory=True)
+
+        key = (device.index, W, H)
+        capacity = max(int(_capacity_hint.get(key, 0)), 4 * P, 1024)
+        while True:
+            binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
+            ws = Workspace(d_geom=geom.data_ptr(), geom_bytes=geom.numel(),
+                           d_image=image.data_ptr(), image_bytes=image.numel(),
+                           d_binning=binning.data_ptr(), binning_bytes=binning.numel(),
+                           binning_capacity=capacity, d_status=status.data_ptr())
+            _lib.check(L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws),
+                                       C.c_void_p(out_color.data_ptr()),
+                                       C.c_void_p(radii.data_ptr()) if P > 0 else None,
+                                       C.c_void_p(stream.cuda_stream)))
+            status_host.copy_(status, non_blocking=True)
+            stream.synchronize()
+            num_rendered = int(status_host[_lib.ST_NUM_RENDERED])
+            if int(status_host[_lib.ST_OVERFLOW]) == 0:
+                break
+            capacity = int(num_rendered * 1.05) + 1024     # exact count known now: one retry suffices
+        _capacity_hint[key] = int(num_rendered * 1.125) + 4096
+
+    call = _Call()
+    call.prm, call.inp, call.ws = prm, inp, ws
+    call.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, view, proj,
+                    campos, vis)
+    call.geom, call.image, call.binning, call.status = geom, image, binning, status
+    call.capacity, call.num_rendered, call.device = capacity, num_rendered, device
+    return out_color, radii, call
+
+
+def _launch_backward(call: "_Call", radii, grad_out_color):
+    L = _lib.lib()
+    prm = call.prm
+    P, M = prm.P, prm.sh_coeffs
+    device = call.device
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device)
+        g = grad_out_color
+        if g.dtype != torch.float32:
+            g = g.float()
+        g = g.contiguous()
+        opts = dict(dtype=torch.float32, device=device)
+        dL_dmeans3D = torch.empty((P, 3), **opts)
+        dL_dmeans2D = torch.empty((P, 3), **opts)
+        dL_dcolors = torch.empty((P, 3), **opts)
+        dL_dopacity = torch.empty((P, 1), **opts)
+        dL_dcov3D = torch.empty((P, 6), **opts)
+        dL_dsh = torch.empty((P, M, 3), **opts)
+        dL_dscales = torch.empty((P, 3), **opts)
+        dL_drotations = torch.empty((P, 4), **opts)
+        grads = Grads(d_dL_dmeans2D=_ptr(dL_dmeans2D), d_dL_dcolors=_ptr(dL_dcolors),
+                      d_dL_dopacity=_ptr(dL_dopacity), d_dL_dmeans3D=_ptr(dL_dmeans3D),
+                      d_dL_dcov3D=_ptr(dL_dcov3D), d_dL_dsh=_ptr(dL_dsh), d_dL_dscales=_ptr(dL_dscales),
+                      d_dL_drotations=_ptr(dL_drotations))
+        _lib.check(L.fb200_backward(C.byref(prm), C.byref(call.inp), C.byref(call.ws),
+                                    C.c_void_p(radii.data_ptr()) if P > 0 else None,
+                                    C.c_void_p(g.data_ptr()), C.byref(grads),
+                                    C.c_void_p(stream.cuda_stream)))
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings, visibility_mask=None):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings, visibility_mask)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings, visibility_mask=None):
+        args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                visibility_mask)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args[:7])   # copy before they can be corrupted
+            try:
+                color, radii, call = _launch_forward(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            color, radii, call = _launch_forward(*args)
+        ctx.call = call
+        ctx.num_rendered = call.num_rendered
+        ctx.raster_settings = raster_settings
+        ctx.present = tuple(t.numel() != 0 for t in (sh, colors_precomp, scales, rotations, cov3Ds_precomp))
+        ctx.save_for_backward(radii)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        (radii,) = ctx.saved_tensors
+        call = ctx.call
+        if ctx.raster_settings.debug:
+            try:
+                out = _launch_backward(call, radii, grad_out_color)
+            except Exception as ex:
+                torch.save(cpu_deep_copy_tuple(call.tensors[:7]) + (grad_out_color.cpu().clone(),), "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            out = _launch_backward(call, radii, grad_out_color)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
+         grad_scales, grad_rotations) = out
+        has_sh, has_col, has_s, has_r, has_cov = ctx.present
+        # same order as DGR/diff_gaussian_rasterization/__init__.py:143-153
+        return (
+            grad_means3D,
+            grad_means2D,
+            grad_sh if has_sh else None,
+            grad_colors_precomp if has_col else None,
+            grad_opacities,
+            grad_scales if has_s else None,
+            grad_rotations if has_r else None,
+            grad_cov3Ds_precomp if has_cov else None,
+            None,
+            None,
+        )
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Boolean mask of points passing the near-plane test (checkFrustum, rasterizer_impl.cu:54-66)."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            if not positions.is_cuda:
+                raise RuntimeError("frosting_b200 runs on CUDA tensors only (no CPU fallback)")
+            device = positions.device
+            pos = _f32c(positions, device, "positions")
+            view = _f32c(rs.viewmatrix, device, "viewmatrix")
+            proj = _f32c(rs.projmatrix, device, "projmatrix")
+            P = pos.size(0)
+            present = torch.empty((P,), dtype=torch.bool, device=device)
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().fb200_mark_visible(
+                    P, _ptr(pos), _ptr(view), _ptr(proj), _ptr(present),
+                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, visibility_mask=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, raster_settings, visibility_mask)
+
+
+# ---- introspection for parity tests ----------------------------------------------------------------------
+def forward_with_state(raster_settings, means3D, opacities, shs=None, colors_precomp=None, scales=None,
+                       rotations=None, cov3D_precomp=None, visibility_mask=None):
+    """Run the forward and expose the internal arrays (no autograd): used by tests to compare depth
+    bits, rects, records, ranges and the sorted point list with the reference's buffers."""
+    e = torch.Tensor([])
+    with torch.no_grad():
+        color, radii, call = _launch_forward(
+            means3D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
+            e if scales is None else scales, e if rotations is None else rotations,
+            e if cov3D_precomp is None else cov3D_precomp, raster_settings, visibility_mask)
+    P, W, H = call.prm.P, call.prm.image_width, call.prm.image_height
+    lay = Layout()
+    _lib.check(_lib.lib().fb200_get_layout(P, W, H, call.capacity, C.byref(lay)))
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    R = call.num_rendered
+
+    def view(buf, off, nbytes, dtype):
+        base = (-buf.data_ptr()) % 128   # the library aligns the base to 128 bytes
+        return buf[base + off: base + off + nbytes].view(dtype)
+
+    st = dict(
+        color=color, radii=radii, num_rendered=R, call=call,
+        rec=view(call.geom, lay.geom_rec, P * 48, torch.float32).view(P, 12),
+        depth=view(call.geom, lay.geom_depth, P * 4, torch.float32),
+        rect=view(call.geom, lay.geom_rect, P * 8, torch.int32).view(P, 2),
+        clamped=view(call.geom, lay.geom_clamped, P, torch.uint8),
+        final_T=view(call.image, lay.img_final_T, W * H * 4, torch.float32).view(H, W),
+        n_contrib=view(call.image, lay.img_n_contrib, W * H * 4, torch.int32).view(H, W),
+        ranges=view(call.image, lay.img_ranges, T * 8, torch.int32).view(T, 2),
+        tile_count=view(call.image, lay.img_tile_count, T * 4, torch.int32),
+        point_list=view(call.binning, lay.bin_point_list, R * 4, torch.int32),
+        keys=view(call.binning, lay.bin_keys, R * 8, torch.int64),
+    )
+    return st

@@ -1,0 +1,176 @@
+/*
+ * frosting_b200.h -- C ABI of the B200-native Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for Frosting's render path.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repository; DGR =
+ * gaussian_splatting/submodules/diff-gaussian-rasterization):
+ *
+ *   fb200_forward        <- _C.rasterize_gaussians          DGR/ext.cpp:16, DGR/rasterize_points.cu:35-115,
+ *                           CudaRasterizer::Rasterizer::forward  DGR/cuda_rasterizer/rasterizer_impl.cu:198-336
+ *   fb200_backward       <- _C.rasterize_gaussians_backward DGR/ext.cpp:17, DGR/rasterize_points.cu:117-196,
+ *                           Rasterizer::backward            DGR/cuda_rasterizer/rasterizer_impl.cu:340-434
+ *   fb200_mark_visible   <- _C.mark_visible                 DGR/ext.cpp:18, DGR/rasterize_points.cu:198-217
+ *   fb200_mesh_visibility<- nvdiff_rasterization / MeshRasterizer.forward
+ *                           frosting_utils/nvdiffrast.py:8-58, frosting_utils/mesh_rasterization.py:109-156
+ *   fb200_*_bytes        <- required<GeometryState|ImageState|BinningState>()
+ *                           DGR/cuda_rasterizer/rasterizer_impl.h:66-72
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No C++/torch types cross this boundary.
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device; the library never
+ *     allocates, frees or retains device memory (the caller owns every buffer, as the reference's
+ *     torch binding does through its resize callbacks, DGR/rasterize_points.cu:27-33).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless `debug` is set (the reference's CHECK_CUDA behaviour, DGR/cuda_rasterizer/auxiliary.h:166-173).
+ *   - return value: 0 on success, negative FB200_E* on error; fb200_last_error() gives the
+ *     message (thread-local).
+ */
+#ifndef FROSTING_B200_H_
+#define FROSTING_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_ABI_VERSION 1
+
+#define FB200_OK 0
+#define FB200_EINVAL (-1)   /* bad argument (shape / null pointer / unsupported channel count) */
+#define FB200_ECUDA (-2)    /* CUDA runtime error (message holds cudaGetErrorString) */
+#define FB200_ENOSPC (-3)   /* a caller-provided workspace is too small */
+
+#define FB200_TILE 16       /* tile edge in pixels: BLOCK_X/BLOCK_Y, DGR/cuda_rasterizer/config.h:16-17 */
+#define FB200_CHANNELS 3    /* NUM_CHANNELS, DGR/cuda_rasterizer/config.h:15 */
+
+/* Per-call scalars: the non-tensor fields of GaussianRasterizationSettings
+ * (DGR/diff_gaussian_rasterization/__init__.py:157-169) plus the tensor extents. */
+typedef struct fb200_params {
+    int32_t P;               /* number of Gaussians (means3D.size(0)) */
+    int32_t sh_degree;       /* D: active SH degree 0..3 */
+    int32_t sh_coeffs;       /* M: coefficients stored per Gaussian (sh.size(1)), 0 if colours are precomputed */
+    int32_t image_width;
+    int32_t image_height;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    int32_t prefiltered;     /* trap if a Gaussian is near-culled (auxiliary.h:156-160) */
+    int32_t debug;           /* synchronise + check after every stage */
+} fb200_params;
+
+/* Device inputs of the forward pass.  Exactly one of (d_shs | d_colors_precomp) and exactly one of
+ * (d_scales + d_rotations | d_cov3D_precomp) must be non-null, as GaussianRasterizer.forward
+ * requires (__init__.py:191-195). */
+typedef struct fb200_inputs {
+    const float* d_background;     /* [3] */
+    const float* d_means3D;        /* [P,3] */
+    const float* d_shs;            /* [P,M,3] or NULL */
+    const float* d_colors_precomp; /* [P,3]   or NULL */
+    const float* d_opacities;      /* [P]   */
+    const float* d_scales;         /* [P,3] or NULL */
+    const float* d_rotations;      /* [P,4] (r,x,y,z), NOT normalised (forward.cu:127) or NULL */
+    const float* d_cov3D_precomp;  /* [P,6] or NULL */
+    const float* d_viewmatrix;     /* [16] as stored by torch: W2C transposed */
+    const float* d_projmatrix;     /* [16] */
+    const float* d_campos;         /* [3]  */
+    const uint8_t* d_visibility;   /* optional [P] mask (0 = drop before tiling): the occlusion-culling
+                                      render_mask of frosting_model.py:1564-1586 applied in place instead
+                                      of by boolean gathers.  NULL = all Gaussians enter. */
+} fb200_inputs;
+
+/* Caller-owned workspaces (sizes from the *_bytes queries; 256-byte aligned base pointers). */
+typedef struct fb200_workspace {
+    void* d_geom;   size_t geom_bytes;     /* per-Gaussian state, kept for backward */
+    void* d_image;  size_t image_bytes;    /* per-pixel + per-tile state, kept for backward */
+    void* d_binning; size_t binning_bytes; /* per-instance state, kept for backward */
+    int64_t binning_capacity;              /* instances the binning buffer was sized for */
+    int32_t* d_status;                     /* [FB200_STATUS_WORDS] device words, see below */
+} fb200_workspace;
+
+/* d_status words written by fb200_forward (stream-ordered; copy back after the call). */
+#define FB200_STATUS_WORDS 8
+#define FB200_ST_NUM_RENDERED 0   /* R = total tile instances (reference: point_offsets[P-1]) */
+#define FB200_ST_OVERFLOW 1       /* 1 if R > binning_capacity: nothing was rendered, grow and call again */
+#define FB200_ST_MAX_TILE 2       /* longest per-tile list */
+#define FB200_ST_NUM_VISIBLE 3    /* Gaussians with radii > 0 */
+
+size_t fb200_geom_bytes(int32_t P);
+size_t fb200_image_bytes(int32_t image_width, int32_t image_height);
+size_t fb200_binning_bytes(int64_t capacity);
+
+/* Forward: preprocess + cull, per-tile bin/sort, front-to-back blend.
+ *   d_out_color [3,H,W] f32, d_radii [P] i32 -- both fully written (no zero-fill needed).
+ * If the instance count exceeds ws->binning_capacity the status word FB200_ST_OVERFLOW is set,
+ * d_radii and FB200_ST_NUM_RENDERED are valid, d_out_color is not; the caller re-runs with a larger
+ * binning buffer (the reference instead blocks on a D2H copy mid-pipeline, rasterizer_impl.cu:280-281). */
+int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                  float* d_out_color, int32_t* d_radii, void* stream);
+
+/* Gradient outputs of the backward pass, shapes as DGR/rasterize_points.cu:151-159.
+ * All are fully written by the call (invisible Gaussians get zeros); no pre-zeroing needed. */
+typedef struct fb200_grads {
+    float* d_dL_dmeans2D;     /* [P,3] (z = 0) */
+    float* d_dL_dcolors;      /* [P,3] */
+    float* d_dL_dopacity;     /* [P,1] */
+    float* d_dL_dmeans3D;     /* [P,3] */
+    float* d_dL_dcov3D;       /* [P,6] */
+    float* d_dL_dsh;          /* [P,M,3] (may be NULL when M == 0) */
+    float* d_dL_dscales;      /* [P,3] */
+    float* d_dL_drotations;   /* [P,4] */
+} fb200_grads;
+
+int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                   const int32_t* d_radii, const float* d_dL_dout_color /* [3,H,W] */,
+                   const fb200_grads* grads, void* stream);
+
+/* present[i] = (W2C * p_i).z > 0.2   (checkFrustum, rasterizer_impl.cu:54-66) */
+int fb200_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmatrix,
+                       const float* d_projmatrix, uint8_t* d_present, void* stream);
+
+/* Occlusion-culling prepass: rasterise a triangle mesh in clip space and report the nearest face per
+ * pixel (replaces nvdiffrast's OpenGL rasteriser, frosting_utils/nvdiffrast.py:42-54).
+ *   d_verts [V,3], d_faces [F,3] i32, d_full_proj [16] (= full_proj_transform as stored by torch)
+ *   d_zbuf  [H*W] u64 scratch
+ *   d_pix_to_face [H*W] i32 : face id or -1 (mesh_rasterization.py:146 `rast_out[...,3] - 1`)
+ *   d_face_visible [F] u8 (optional) : 1 if the face owns at least one pixel; if `mark_last_on_bg`
+ *     the last face is also marked when any pixel is background, reproducing the `_index_mask[-1]`
+ *     quirk of frosting_model.py:1565-1570. */
+int fb200_mesh_visibility(int32_t V, int32_t F, const float* d_verts, const int32_t* d_faces,
+                          const float* d_full_proj, int32_t image_width, int32_t image_height,
+                          uint64_t* d_zbuf, int32_t* d_pix_to_face, uint8_t* d_face_visible,
+                          int32_t mark_last_on_bg, void* stream);
+
+/* render_mask[i] = face_visible[cell[i]] for i < n_cells_points, 1 for the trailing background
+ * Gaussians (frosting_model.py:1571-1576). */
+int fb200_gaussian_mask_from_faces(int32_t n_points, const int64_t* d_point_cell_indices,
+                                   int32_t F, const uint8_t* d_face_visible, int32_t n_background,
+                                   uint8_t* d_mask, void* stream);
+
+/* Introspection for parity tests: byte offsets of the internal arrays inside the caller's buffers,
+ * so tests can compare depth bits / rects / records / ranges / point_list with the reference's
+ * geomBuffer / binningBuffer / imgBuffer one-to-one. */
+typedef struct fb200_layout {
+    size_t geom_rec;       /* float4[3P]: {x,y,conic.x,conic.y},{conic.z,opacity,r,g},{b,ext_x,ext_y,depth} */
+    size_t geom_depth;     /* f32[P]  view-space z (sort key bits) */
+    size_t geom_rect;      /* u32[2P] (min.x | min.y<<16, max.x | max.y<<16) in tiles */
+    size_t geom_clamped;   /* u8[P]   bit c = colour channel c was clamped */
+    size_t img_final_T;    /* f32[H*W] */
+    size_t img_n_contrib;  /* u32[H*W] */
+    size_t img_ranges;     /* u32[2T]  (start,end) per tile, (0,0) for empty tiles */
+    size_t img_tile_count; /* u32[T] */
+    size_t bin_point_list; /* u32[capacity] sorted Gaussian index per instance */
+    size_t bin_keys;       /* u64[capacity] (depth_bits<<32 | gaussian idx), sorted within each tile */
+} fb200_layout;
+
+int fb200_get_layout(int32_t P, int32_t image_width, int32_t image_height, int64_t capacity,
+                     fb200_layout* out);
+
+const char* fb200_last_error(void);
+int fb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FROSTING_B200_H_ */
