@@ -135,6 +135,7 @@ int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_w
     a.counters = reinterpret_cast<uint32_t*>(im + il.counters);
     a.point_list = bn ? reinterpret_cast<uint32_t*>(bn + bl.point_list) : nullptr;
     a.keys = bn ? reinterpret_cast<unsigned long long*>(bn + bl.keys) : nullptr;
+    a.keys_scratch = bn ? reinterpret_cast<unsigned long long*>(bn + bl.keys_scratch) : nullptr;
     a.capacity = ws->binning_capacity;
     a.status = ws->d_status;
     a.out_color = d_out_color;

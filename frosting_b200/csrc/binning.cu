@@ -70,8 +70,7 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
         cursor[t] = run;
         if (c > 1) {
             if (c <= (uint32_t)kSortSmallMax) list_small[atomicAdd(&s_n[0], 1u)] = t;
-            else if (c <= (uint32_t)kSortLargeMax) list_large[atomicAdd(&s_n[1], 1u)] = t;
-            else list_huge[atomicAdd(&s_n[2], 1u)] = t;
+            else list_large[atomicAdd(&s_n[1], 1u)] = t;
         }
         run += c;
     }
@@ -86,75 +85,192 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
 }
 
 // ---- scatter: one (depth_bits<<32 | idx) key per (Gaussian, tile) into the tile's segment ----------
+// Warp-balanced expansion: a warp owns 32 consecutive Gaussians, scans their tile counts and then walks
+// the concatenated instance list 32 instances at a time, so a splat covering 1000 tiles costs the warp
+// 32 steps instead of stalling one lane for 1000 dependent atomic round trips (the reference's
+// duplicateWithKeys has the same per-thread double loop, rasterizer_impl.cu:98-108).
 __global__ void __launch_bounds__(256)
 scatter_kernel(int P, int tiles_x, const uint2* __restrict__ rect, const float* __restrict__ depth,
                uint32_t* __restrict__ cursor, u64* __restrict__ keys, const int32_t* __restrict__ status) {
     if (status[FB200_ST_OVERFLOW]) return;
+    const unsigned full = 0xffffffffu;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const uint2 r = rect[idx];
-    const uint32_t minx = r.x & 0xffffu, miny = r.x >> 16, maxx = r.y & 0xffffu, maxy = r.y >> 16;
-    if (maxx <= minx || maxy <= miny) return;
-    const u64 key = ((u64)__float_as_uint(depth[idx]) << 32) | (uint32_t)idx;
-    for (uint32_t ty = miny; ty < maxy; ++ty)
-        for (uint32_t tx = minx; tx < maxx; ++tx) {
+    const int lane = threadIdx.x & 31;
+    uint32_t minx = 0, miny = 0, w = 0, n = 0, dbits = 0;
+    if (idx < P) {
+        const uint2 r = rect[idx];
+        minx = r.x & 0xffffu; miny = r.x >> 16;
+        const uint32_t maxx = r.y & 0xffffu, maxy = r.y >> 16;
+        if (maxx > minx && maxy > miny) {
+            w = maxx - minx;
+            n = w * (maxy - miny);
+            dbits = __float_as_uint(depth[idx]);
+        }
+    }
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - n;
+    const uint32_t total = __shfl_sync(full, incl, 31);
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t item = base + lane;
+        // owner = number of lanes whose inclusive count is <= item
+        int pos = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t v = __shfl_sync(full, incl, pos + step - 1);
+            if (v <= item) pos += step;
+        }
+        const int owner = min(pos, 31);
+        const uint32_t o_excl = __shfl_sync(full, excl, owner);
+        const uint32_t o_minx = __shfl_sync(full, minx, owner);
+        const uint32_t o_miny = __shfl_sync(full, miny, owner);
+        const uint32_t o_w = __shfl_sync(full, w, owner);
+        const uint32_t o_d = __shfl_sync(full, dbits, owner);
+        if (item < total) {
+            const uint32_t k = item - o_excl;
+            const uint32_t ty = o_miny + k / o_w, tx = o_minx + k % o_w;
+            const uint32_t gidx = (uint32_t)(idx - lane + owner);
             const uint32_t slot = atomicAdd(cursor + ty * tiles_x + tx, 1u);
-            keys[slot] = key;
-        }
-}
-
-// ---- per-tile sort ----------------------------------------------------------------------------------
-// Bitonic network in the "flip" formulation: every compare-exchange puts the smaller key at the
-// lower index, so a virtual +inf padding beyond n is a no-op and arbitrary n needs no padding.
-template <int kThreads>
-__device__ __forceinline__ void bitonic_sort_shared(u64* __restrict__ s, int n) {
-    int m = 2;
-    while (m < n) m <<= 1;   // virtual power-of-two size
-    for (int k = 2; k <= m; k <<= 1) {
-        // flip step: partner = i ^ (k-1)
-        for (int t = threadIdx.x; t < (m >> 1); t += kThreads) {
-            const int blk = t / (k >> 1), off = t % (k >> 1);
-            const int i = blk * k + off;
-            const int l = blk * k + (k - 1 - off);
-            if (l < n) {
-                const u64 a = s[i], b = s[l];
-                if (a > b) { s[i] = b; s[l] = a; }
-            }
-        }
-        __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (m >> 1); t += kThreads) {
-                const int i = ((t / j) * (j << 1)) + (t % j);
-                const int l = i + j;
-                if (l < n) {
-                    const u64 a = s[i], b = s[l];
-                    if (a > b) { s[i] = b; s[l] = a; }
-                }
-            }
-            __syncthreads();
+            keys[slot] = ((u64)o_d << 32) | gidx;
         }
     }
 }
 
-template <int kThreads, int kMaxN, bool kDynamic>
+// ---- per-tile sort ----------------------------------------------------------------------------------
+// Stable LSD radix sort of one tile's keys on the 32 depth bits (4 passes of 8 bits; a pass whose digit
+// is the same for every key is skipped), followed by a fix-up that orders runs of EQUAL depth by
+// Gaussian index -- together the total order (depth_bits, idx) of the reference's stable global sort.
+// Ranking is warp-synchronous: each warp owns a contiguous slice of the list, walks it 32 keys at a
+// time and ranks equal digits with __match_any_sync, so no per-key shared-memory atomics are needed.
+// kShared: ping-pong buffers in shared memory (lists up to kMaxN), else in global memory (L2) with a
+// caller-provided scratch array, for lists of any length.
+template <int kThreads>
+// NOTE: no __restrict__ on any of these pointers -- they are written by other threads of the CTA and
+// re-read after barriers; with __restrict__ nvcc forwards a thread's own stale store across
+// __syncthreads() (observed: s_misc[0] kept in a register, threads disagreeing on `skip`, deadlock).
+__device__ __forceinline__ void radix_sort_tile(u64* a, u64* b, int n,
+                                                uint32_t* counters /* [kThreads/32][256] */,
+                                                volatile uint32_t* s_misc, u64*& result) {
+    constexpr int kWarps = kThreads / 32;
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // contiguous slice per warp, multiple of 32
+    const int seg = (((n + kWarps - 1) / kWarps) + 31) & ~31;
+    const int seg_lo = min(n, warp * seg), seg_hi = min(n, seg_lo + seg);
+    u64* src = a;
+    u64* dst = b;
+    for (int shift = 32; shift < 64; shift += 8) {
+        for (int i = tid; i < kWarps * 256; i += kThreads) counters[i] = 0;
+        __syncthreads();
+        // 1. per-warp digit histogram of its slice
+        for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
+            const int i = i0 + lane;
+            const bool have = i < seg_hi;
+            const uint32_t d = have ? (uint32_t)(src[i] >> shift) & 0xffu : 0x100u + lane;   // unique when idle
+            const unsigned peers = __match_any_sync(full, d);
+            if (have && (__ffs(peers) - 1) == lane) counters[warp * 256 + d] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // 2. digit totals, uniform-digit test, exclusive offsets per (digit, warp)
+        if (tid == 0) s_misc[0] = 0;
+        __syncthreads();
+        uint32_t tot = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += counters[w * 256 + tid];
+            if (tot == (uint32_t)n) s_misc[0] = 1;   // every key has this digit: pass is the identity
+        }
+        __syncthreads();
+        const bool skip = s_misc[0] != 0;
+        if (!skip) {
+            // block exclusive scan of tot over the 256 digits (threads 0..255 = 8 warps)
+            uint32_t incl = tot;
+            if (tid < 256) {
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(full, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) s_misc[1 + warp] = incl;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t base = incl - tot;
+                for (int w = 0; w < warp; ++w) base += s_misc[1 + w];
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) {
+                    const uint32_t c = counters[w * 256 + tid];
+                    counters[w * 256 + tid] = base;
+                    base += c;
+                }
+            }
+            __syncthreads();
+            // 3. stable scatter
+            for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
+                const int i = i0 + lane;
+                const bool have = i < seg_hi;
+                const u64 k = have ? src[i] : 0ull;
+                const uint32_t d = have ? (uint32_t)(k >> shift) & 0xffu : 0x100u + lane;
+                const unsigned peers = __match_any_sync(full, d);
+                uint32_t off = 0;
+                if (have) off = counters[warp * 256 + d] + __popc(peers & ((1u << lane) - 1u));
+                __syncwarp();
+                if (have) {
+                    dst[off] = k;
+                    if ((__ffs(peers) - 1) == lane) counters[warp * 256 + d] += __popc(peers);
+                }
+                __syncwarp();
+            }
+            u64* t = src; src = dst; dst = t;
+        }
+        __syncthreads();
+    }
+    // 4. order runs of equal depth by Gaussian index (rare: exact float ties)
+    for (int i = tid; i < n; i += kThreads) {
+        const uint32_t d = (uint32_t)(src[i] >> 32);
+        const bool run_start = (i == 0 || (uint32_t)(src[i - 1] >> 32) != d) && (i + 1 < n) &&
+                               (uint32_t)(src[i + 1] >> 32) == d;
+        if (run_start) {
+            int e = i + 1;
+            while (e < n && (uint32_t)(src[e] >> 32) == d) ++e;
+            for (int x = i + 1; x < e; ++x) {          // insertion sort of the run [i, e)
+                const u64 kx = src[x];
+                int y = x - 1;
+                while (y >= i && src[y] > kx) { src[y + 1] = src[y]; --y; }
+                src[y + 1] = kx;
+            }
+        }
+    }
+    __syncthreads();
+    result = src;
+}
+
+template <int kThreads, int kMaxN>
 __global__ void __launch_bounds__(kThreads)
 tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
                         const uint2* __restrict__ ranges, u64* __restrict__ keys,
                         uint32_t* __restrict__ point_list, const int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ u64 stat_smem[kDynamic ? 1 : kMaxN];
-    u64* s = kDynamic ? reinterpret_cast<u64*>(dyn_smem) : stat_smem;
+    __shared__ u64 buf_a[kMaxN];
+    __shared__ u64 buf_b[kMaxN];
+    __shared__ uint32_t counters[(kThreads / 32) * 256];
+    __shared__ uint32_t s_misc[16];
     if (status[FB200_ST_OVERFLOW]) return;
     const uint32_t count = *n_list;
     for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
         const uint2 rg = ranges[list[w]];
         const int n = (int)(rg.y - rg.x);
         u64* g = keys + rg.x;
-        for (int i = threadIdx.x; i < n; i += kThreads) s[i] = g[i];
+        for (int i = threadIdx.x; i < n; i += kThreads) buf_a[i] = g[i];
         __syncthreads();
-        bitonic_sort_shared<kThreads>(s, n);
+        u64* res;
+        radix_sort_tile<kThreads>(buf_a, buf_b, n, counters, s_misc, res);
         for (int i = threadIdx.x; i < n; i += kThreads) {
-            const u64 k = s[i];
+            const u64 k = res[i];
             g[i] = k;
             point_list[rg.x + i] = (uint32_t)k;
         }
@@ -162,19 +278,28 @@ tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __res
     }
 }
 
-// Lists longer than the shared-memory classes: same network directly on global memory (L2).
-__global__ void __launch_bounds__(1024)
+// Lists longer than the shared-memory class: same algorithm, ping-pong between the key array and a
+// scratch array in global memory (L2-resident for any realistic tile).
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
 tile_sort_global_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
-                        const uint2* __restrict__ ranges, u64* __restrict__ keys,
+                        const uint2* __restrict__ ranges, u64* __restrict__ keys, u64* __restrict__ scratch,
                         uint32_t* __restrict__ point_list, const int32_t* __restrict__ status) {
+    __shared__ uint32_t counters[(kThreads / 32) * 256];
+    __shared__ uint32_t s_misc[40];
     if (status[FB200_ST_OVERFLOW]) return;
     const uint32_t count = *n_list;
     for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
         const uint2 rg = ranges[list[w]];
         const int n = (int)(rg.y - rg.x);
         u64* g = keys + rg.x;
-        bitonic_sort_shared<1024>(g, n);   // same code, global pointer; __syncthreads orders the stages
-        for (int i = threadIdx.x; i < n; i += 1024) point_list[rg.x + i] = (uint32_t)g[i];
+        u64* res;
+        radix_sort_tile<kThreads>(g, scratch + rg.x, n, counters, s_misc, res);
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const u64 k = res[i];
+            if (res != g) g[i] = k;
+            point_list[rg.x + i] = (uint32_t)k;
+        }
         __syncthreads();
     }
 }
@@ -200,26 +325,17 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
         scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a.prm.P, a.tiles_x, a.rect, a.depth, a.cursor,
                                                              a.keys, a.status);
     single_instance_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, a.ranges, a.keys, a.point_list, a.status);
-    // grid sizes: the work lists live on the device, so launch enough CTAs for the worst case and
-    // let each CTA stride over the list.
+    // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides
+    // over its list.
     {
-        const int grid = min(T, 148 * 8);
-        tile_sort_shared_kernel<256, kSortSmallMax, false><<<grid, 256, 0, s>>>(
+        const int grid = min(T, 148 * 5);
+        tile_sort_shared_kernel<256, kSortSmallMax><<<grid, 256, 0, s>>>(
             a.list_small, a.counters + 0, a.ranges, a.keys, a.point_list, a.status);
     }
     {
-        const int smem = kSortLargeMax * 8;
-        cudaError_t e = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortLargeMax, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        const int grid = min(T, 148);
-        tile_sort_shared_kernel<1024, kSortLargeMax, true><<<grid, 1024, smem, s>>>(
-            a.list_large, a.counters + 1, a.ranges, a.keys, a.point_list, a.status);
-    }
-    {
-        const int grid = min(T, 148);
-        tile_sort_global_kernel<<<grid, 1024, 0, s>>>(a.list_huge, a.counters + 2, a.ranges, a.keys,
-                                                      a.point_list, a.status);
+        const int grid = min(T, 148 * 2);
+        tile_sort_global_kernel<1024><<<grid, 1024, 0, s>>>(a.list_large, a.counters + 1, a.ranges, a.keys,
+                                                            a.keys_scratch, a.point_list, a.status);
     }
     return cudaGetLastError();
 }

@@ -64,8 +64,8 @@ geom_bwd_kernel(BwdArgs a) {
     V3 g_scale = v3(0.f, 0.f, 0.f);
     float4 g_rot = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const bool has_sh = a.in.d_shs != nullptr && M > 0;
     float* dsh = (a.g.d_dL_dsh != nullptr && M > 0) ? a.g.d_dL_dsh + i * M * 3 : nullptr;
+    const bool has_sh = a.in.d_shs != nullptr && M > 0 && dsh != nullptr;
 
     if (visible) {
         const float4* accp = reinterpret_cast<const float4*>(a.acc + i * 12);
@@ -196,23 +196,48 @@ geom_bwd_kernel(BwdArgs a) {
             }
             const int ncoef = (D + 1) * (D + 1);
             V3 dcdx = v3(0.f, 0.f, 0.f), dcdy = v3(0.f, 0.f, 0.f), dcdz = v3(0.f, 0.f, 0.f);
+            const float dR[3] = {dRGB.x, dRGB.y, dRGB.z};
+            float ax[3] = {0.f, 0.f, 0.f}, ay[3] = {0.f, 0.f, 0.f}, az[3] = {0.f, 0.f, 0.f};
+            if (M == 16) {
+                // 192 B per Gaussian in and out: twelve 128-bit loads and stores instead of 48 + 48
+                // scalar accesses at a 192-byte lane stride (those were LSU-bound).
+                const float4* sh4 = reinterpret_cast<const float4*>(sh);
+                float4* dsh4 = reinterpret_cast<float4*>(dsh);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < M) {
-                    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-                    if (k < ncoef) {
-                        o0 = bv[k] * dRGB.x; o1 = bv[k] * dRGB.y; o2 = bv[k] * dRGB.z;
-                        if (k > 0) {
-                            const float s0 = sh[3 * k], s1 = sh[3 * k + 1], s2 = sh[3 * k + 2];
-                            dcdx.x += bx[k] * s0; dcdx.y += bx[k] * s1; dcdx.z += bx[k] * s2;
-                            dcdy.x += by[k] * s0; dcdy.y += by[k] * s1; dcdy.z += by[k] * s2;
-                            dcdz.x += bz[k] * s0; dcdz.y += bz[k] * s1; dcdz.z += bz[k] * s2;
+                for (int q = 0; q < 12; ++q) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (4 * q < 3 * ncoef) {
+                        const float4 s4 = __ldg(sh4 + q);
+                        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = (4 * q + e) / 3, c = (4 * q + e) % 3;
+                            if (k < ncoef) {
+                                o[e] = bv[k] * dR[c];
+                                ax[c] += bx[k] * sv[e]; ay[c] += by[k] * sv[e]; az[c] += bz[k] * sv[e];
+                            }
                         }
+                    }
+                    dsh4[q] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            } else {
+                for (int k = 0; k < M; ++k) {
+                    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+                    if (k < ncoef && k < 16) {
+                        float bvk = 0.f, bxk = 0.f, byk = 0.f, bzk = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j == k) { bvk = bv[j]; bxk = bx[j]; byk = by[j]; bzk = bz[j]; }
+                        o0 = bvk * dR[0]; o1 = bvk * dR[1]; o2 = bvk * dR[2];
+                        const float s0 = sh[3 * k], s1 = sh[3 * k + 1], s2 = sh[3 * k + 2];
+                        ax[0] += bxk * s0; ax[1] += bxk * s1; ax[2] += bxk * s2;
+                        ay[0] += byk * s0; ay[1] += byk * s1; ay[2] += byk * s2;
+                        az[0] += bzk * s0; az[1] += bzk * s1; az[2] += bzk * s2;
                     }
                     dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
                 }
             }
-            for (int k = 16; k < M; ++k) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+            dcdx = v3(ax[0], ax[1], ax[2]); dcdy = v3(ay[0], ay[1], ay[2]); dcdz = v3(az[0], az[1], az[2]);
             // through dir = dorig / |dorig|:  d/dv = (dv |v|^2 - v (v . dv)) / |v|^3
             const V3 ddir = v3(dot(dcdx, dRGB), dot(dcdy, dRGB), dot(dcdz, dRGB));
             const float sum2 = dot(dorig, dorig);
@@ -243,23 +268,23 @@ geom_bwd_kernel(BwdArgs a) {
                 gs[r] = acc_s;
             }
             g_scale = v3(gs[0], gs[1], gs[2]);
-            // Rm[0][1] = 2(xy+rz), Rm[0][2] = 2(xz-ry), Rm[1][0] = 2(xy-rz), Rm[1][2] = 2(yz+rx),
-            // Rm[2][0] = 2(xz+ry), Rm[2][1] = 2(yz-rx); the reference indexes dL_dMt[a][b] with
-            // a = row of its S (our r) and b = column index of glm R^T ... expressed here directly:
-            // H[a][b] := dL/d(R_glm[b][a]) where R_glm[b][a] = Rm[a][b]^T convention of backward.cu:296-300
-            // -> H[a][b] = Gm[a][b] with Rm_ref(a,b) = R_glm[b][a].  R_glm[col][row]: col0 = (1-2(yy+zz), 2(xy-rz), 2(xz+ry))
-            // so Rm_ref(0,1) = R_glm[1][0] = 2(xy+rz) = Rm[0][1].  Identical indexing.
+            // Hm[a][b] = dL/dRm[a][b]; the four sums below are dRm/dq contracted with it.
             const float (&Hm)[3][3] = Gm;
             g_rot.x = 2.f * qz * (Hm[0][1] - Hm[1][0]) + 2.f * qy * (Hm[2][0] - Hm[0][2]) + 2.f * qx * (Hm[1][2] - Hm[2][1]);
             g_rot.y = 2.f * qy * (Hm[1][0] + Hm[0][1]) + 2.f * qz * (Hm[2][0] + Hm[0][2]) + 2.f * qr * (Hm[1][2] - Hm[2][1]) - 4.f * qx * (Hm[2][2] + Hm[1][1]);
             g_rot.z = 2.f * qx * (Hm[1][0] + Hm[0][1]) + 2.f * qr * (Hm[2][0] - Hm[0][2]) + 2.f * qz * (Hm[1][2] + Hm[2][1]) - 4.f * qy * (Hm[2][2] + Hm[0][0]);
             g_rot.w = 2.f * qr * (Hm[0][1] - Hm[1][0]) + 2.f * qx * (Hm[2][0] + Hm[0][2]) + 2.f * qy * (Hm[1][2] + Hm[2][1]) - 4.f * qz * (Hm[1][1] + Hm[0][0]);
         }
-    } else if (dsh != nullptr) {
-        for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
     }
-    if (visible && !has_sh && dsh != nullptr)
-        for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
+    if ((!visible || !has_sh) && dsh != nullptr) {
+        if (M == 16) {
+            float4* dsh4 = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) dsh4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
+        }
+    }
 
     a.g.d_dL_dmeans2D[3 * i] = g_mean2d_x; a.g.d_dL_dmeans2D[3 * i + 1] = g_mean2d_y; a.g.d_dL_dmeans2D[3 * i + 2] = 0.f;
     a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z;

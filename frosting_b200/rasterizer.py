@@ -45,6 +45,18 @@ _capacity_hint = {}
 NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove it is output-neutral
 
 
+_pinned = {}
+
+
+def _pinned_status(device):
+    # one pinned 32-byte mailbox per device: cudaHostAlloc per call would cost more than the frame
+    t = _pinned.get(device.index)
+    if t is None:
+        t = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, pin_memory=True)
+        _pinned[device.index] = t
+    return t
+
+
 def _ptr(t: Optional[torch.Tensor]):
     if t is None or t.numel() == 0:
         return None
@@ -114,7 +126,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
         geom = torch.empty((L.fb200_geom_bytes(P),), dtype=torch.uint8, device=device)
         image = torch.empty((L.fb200_image_bytes(W, H),), dtype=torch.uint8, device=device)
         status = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, device=device)
-        status_host = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, pin_memory=True)
+        status_host = _pinned_status(device)
 
         key = (device.index, W, H)
         capacity = max(int(_capacity_hint.get(key, 0)), 4 * P, 1024)

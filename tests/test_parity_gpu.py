@@ -247,3 +247,23 @@ def test_long_tile_lists_all_sort_classes(cuda_device):
     assert torch.equal(st["point_list"], refdgr.binning_views(ref["binning"], R)["point_list"])
     assert torch.equal(st["n_contrib"], refdgr.img_views(ref["img"], H, W)["n_contrib"])
     assert (st["color"] - ref["color"]).abs().max().item() <= 1e-4
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref not built")
+def test_equal_depth_ties_follow_gaussian_index(cuda_device):
+    """Exact depth ties: the reference's stable radix sort keeps ascending Gaussian index
+    (rasterizer_impl.cu:98-108 emission order); our per-tile sort must reproduce it."""
+    dev = cuda_device
+    P, W, H = 30_000, 160, 128
+    from frosting_b200 import scenes
+    cam = scenes.make_camera(W, H, device=dev)
+    g = scenes.random_gaussians(P, cam, 5, device=dev, large_frac=0.0, near_frac=0.0)
+    g["means3D"][:, 2] = torch.tensor([3.0, 4.0, 5.0, 4.0], device=dev).repeat(P // 4)   # only 3 distinct depths
+    rs = scenes.settings_for(cam, 0, device=dev)
+    ref = refdgr.forward(rs, g["means3D"], g["opacities"], shs=g["shs"], scales=g["scales"], rotations=g["rotations"])
+    st = fb.forward_with_state(rs, g["means3D"], g["opacities"], shs=g["shs"], scales=g["scales"], rotations=g["rotations"])
+    R = ref["num_rendered"]
+    assert st["num_rendered"] == R
+    assert torch.equal(st["point_list"], refdgr.binning_views(ref["binning"], R)["point_list"])
+    assert torch.equal(st["n_contrib"], refdgr.img_views(ref["img"], H, W)["n_contrib"])
+    assert (st["color"] - ref["color"]).abs().max().item() <= 1e-4
