@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward frames/sec of the render path on BASELINE.json's headline config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config C3 of BASELINE.json): 2 M frosting-layer Gaussians bound to the prism cells of a ~1 M-face
+UV-sphere shell (frosting_b200/scenes.py), occlusion culling ON, 1920x1080, SH degree 3, synthetic data,
+random-init parameters.  A "step" is one frame: occlusion mask -> rasterizer forward -> scalar loss
+(color * G).sum() -> backward to means3D / SH / opacity / scale / rotation (+ the means2D sink), for one
+camera; every rank owns 8 cameras on a ring (config C4's sharding: camera batch split across GPUs, Gaussians
+replicated, the only collective is the NCCL all-reduce of the scalar loss) and cycles through them, so
+per-GPU work is fixed as N grows ("weak" scaling).  `value` = frames all ranks finished / max-over-ranks time.
+
+--impl reference runs the UNMODIFIED reference rasterizer compiled from /root/reference into oracle/_ref
+(oracle/build_ref.py) through its own entry points, with Frosting's boolean-gather masking
+(frosting_scene/frosting_model.py:1564-1586) in torch, on the same scene, cameras and loss.  The reference
+has no CPU implementation of this path; its own CUDA code is the stock code path.
+
+Timing: CUDA events around exactly K steps after W warm-up steps, barrier + synchronize on both sides, max
+over ranks.  Inputs are larger than L2 (472 MB of attributes are read per frame, 126 MB L2), no flush needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd frames/sec @2M Gaussians 1080p"
+UNIT = "frames/s"
+
+WORKLOADS = {
+    # name: (P, W, H, sh_degree, kind, seed)
+    "c3": (2_000_000, 1920, 1080, 3, "frosting", 1237),
+    "c2": (500_000, 800, 800, 3, "random", 1236),
+    "c5": (6_000_000, 1600, 1200, 3, "random", 1239),
+    "tiny": (20_000, 320, 240, 3, "frosting", 1),
+}
+CAMS_PER_GPU = 8
+RING_RADIUS = 10.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15]
+        if not rows:
+            rows = [l.split(", ") for (_, l) in self.lines[-3:]]
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, device, rank, world):
+    from frosting_b200 import scenes
+    P, W, H, D, kind, seed = WORKLOADS[name]
+    n_cams = CAMS_PER_GPU * world
+    cam0 = scenes.make_camera(W, H, device=device)
+    if kind == "frosting":
+        # ring of radius 10 around the shell (radius 3): the whole object is in frame, ~26 % of the Gaussians
+        # survive occlusion culling, R ~ 1.6 M tile instances per frame
+        cams = scenes.ring_cameras(n_cams, W, H, radius=RING_RADIUS, device=device)[
+            rank * CAMS_PER_GPU:(rank + 1) * CAMS_PER_GPU]
+    else:
+        cams = [cam0] * CAMS_PER_GPU   # free Gaussians are generated inside cam0's frustum
+    wl = dict(name=name, P=P, W=W, H=H, D=D, kind=kind, cams=cams)
+    t = time.time()
+    if kind == "frosting":
+        params, mesh = scenes.frosting_layer(P, cam0, seed, n_faces_target=max(1000, P // 2), device="cpu")
+        attrs = scenes.frosting_attributes(params, mesh)
+        wl["mesh"] = {k: v.to(device) for k, v in mesh.items()}
+    else:
+        attrs = scenes.random_gaussians(P, cam0, seed, device="cpu")
+        # spread the free Gaussians around the ring centre so every ring camera sees a similar load
+        wl["mesh"] = None
+    wl["attrs"] = {k: v.to(device).contiguous() for k, v in attrs.items()}
+    g = torch.Generator().manual_seed(4321 + rank)
+    wl["cot_host"] = [torch.randn(3, H, W, generator=g).pin_memory() for _ in range(len(cams))]
+    wl["gen_s"] = time.time() - t
+    return wl
+
+
+def precompute_visibility(wl, device):
+    """Visible-face set per camera, once, as Frosting's refinement does (frosting_trainers/refine.py:430-441)."""
+    import frosting_b200 as fb
+    if wl["mesh"] is None:
+        wl["face_visible"] = None
+        return
+    vis = []
+    for cam in wl["cams"]:
+        _, fv, _ = fb.rasterize_mesh(wl["mesh"]["verts"], wl["mesh"]["faces"], cam.full_proj_transform,
+                                     cam.image_height, cam.image_width, mark_last_on_bg=True)
+        vis.append(fv.to(torch.uint8).contiguous())
+    wl["face_visible"] = vis
+
+
+class OursStep:
+    def __init__(self, wl, device):
+        import frosting_b200 as fb
+        from frosting_b200 import scenes
+        self.fb, self.scenes, self.wl, self.device = fb, scenes, wl, device
+        self.leaves = {k: v.clone().requires_grad_(True) for k, v in wl["attrs"].items()}
+        self.P = wl["P"]
+        self.last_R = 0
+
+    def settings(self, cam):
+        return self.scenes.settings_for(cam, self.wl["D"], device=self.device)
+
+    def __call__(self, i, rs, cot):
+        fb, L = self.fb, self.leaves
+        for v in L.values():
+            v.grad = None                                        # zero_grad(set_to_none=True), refine.py:522
+        mask = None
+        if self.wl["face_visible"] is not None:
+            mask = fb.gaussian_render_mask(self.wl["face_visible"][i], self.wl["mesh"]["cells"], self.P)
+        means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)   # frosting_model.py:1624
+        color, radii = fb.GaussianRasterizer(rs)(
+            means3D=L["means3D"], means2D=means2D, opacities=L["opacities"], shs=L["shs"], scales=L["scales"],
+            rotations=L["rotations"], visibility_mask=mask)
+        loss = (color * cot).sum()
+        loss.backward()
+        return loss.detach()
+
+
+class ReferenceStep:
+    def __init__(self, wl, device):
+        from oracle import refdgr
+        from frosting_b200 import scenes
+        refdgr.module()
+        self.refdgr, self.scenes, self.wl, self.device = refdgr, scenes, wl, device
+        self.leaves = {k: v.clone().requires_grad_(True) for k, v in wl["attrs"].items()}
+        self.masks = None
+        if wl["face_visible"] is not None:
+            self.cells = wl["mesh"]["cells"]
+
+    def settings(self, cam):
+        return self.scenes.settings_for(cam, self.wl["D"], device=self.device)
+
+    def __call__(self, i, rs, cot):
+        L = self.leaves
+        for v in L.values():
+            v.grad = None
+        m3, op, sh, sc, ro = L["means3D"], L["opacities"], L["shs"], L["scales"], L["rotations"]
+        if self.wl["face_visible"] is not None:
+            # frosting_model.py:1564-1586: _index_mask[_point_cell_indices], then boolean gathers
+            render_mask = self.wl["face_visible"][i].bool()[self.cells]
+            m3, op, sh, sc, ro = m3[render_mask], op[render_mask], sh[render_mask], sc[render_mask], ro[render_mask]
+        means2D = torch.zeros_like(m3, requires_grad=True)
+        color, radii = self.refdgr.RefRasterize.apply(m3, means2D, sh, op, sc, ro, rs)
+        loss = (color * cot).sum()
+        loss.backward()
+        return loss.detach()
+
+
+def timed_loop(step, wl, device, steps, warmup, world, e2e):
+    """Returns seconds for exactly `steps` steps (max over ranks)."""
+    cams = wl["cams"]
+    n = len(cams)
+    copy_stream = torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+    if not e2e:
+        rs_dev = [step.settings(c) for c in cams]
+        cot_dev = [c.to(device) for c in wl["cot_host"]]
+
+    def fetch(i):
+        """H2D of step inputs from pinned host memory on the copy stream (double-buffered)."""
+        cam = cams[i % n]
+        with torch.cuda.stream(copy_stream):
+            cot = wl["cot_host"][i % n].to(device, non_blocking=True)
+            rs = step.settings(cam)   # camera tensors: created from host values -> H2D (frosting_model.py:1431-1444)
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return rs, cot, ev
+
+    def run(k_steps, offset):
+        losses = []
+        nxt = fetch(offset) if e2e else None
+        for k in range(k_steps):
+            i = (offset + k) % n
+            if e2e:
+                rs, cot, ev = nxt
+                cur.wait_event(ev)
+                cot.record_stream(cur)
+                if k + 1 < k_steps:
+                    nxt = fetch(offset + k + 1)
+            else:
+                rs, cot = rs_dev[i], cot_dev[i]
+            loss = step(i, rs, cot)
+            if world > 1:
+                dist.all_reduce(loss)                      # the path's only collective: scalar loss over NVLink
+            if e2e:
+                losses.append(float(loss.item()))          # D2H read of the step's result, every step
+        return losses
+
+    if not getattr(step, "primed", False):
+        # untimed priming pass over every camera of this rank (each has its own visible set, hence its own
+        # tensor sizes): the caching allocator and the capacity hints settle before the W warm-up steps
+        run(2 * n, 0)
+        step.primed = True
+    run(warmup, 0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from frosting_b200 import _lib
+    l0 = _lib.kernel_launches()
+    t0 = time.time()
+    a.record()
+    run(steps, warmup)
+    b.record()
+    torch.cuda.synchronize(device)
+    timed_loop.launches = _lib.kernel_launches() - l0
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    secs = a.elapsed_time(b) / 1e3
+    if world > 1:
+        t = torch.tensor([secs], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    return secs, t0, t1
+
+
+def stage_profile(step, wl, device, steps):
+    """Average device time of each kernel stage (CUDA events on the launching stream, inside the library)."""
+    from frosting_b200 import _lib
+    cams = wl["cams"]
+    rs_dev = [step.settings(c) for c in cams]
+    cot_dev = [c.to(device) for c in wl["cot_host"]]
+    _lib.profile_enable(True)
+    acc = {k: 0.0 for k in _lib.STAGES}
+    Rs = []
+    try:
+        for k in range(steps):
+            i = k % len(cams)
+            step(i, rs_dev[i], cot_dev[i])
+            torch.cuda.synchronize(device)
+            for kk, v in _lib.profile_read().items():
+                acc[kk] += v
+            Rs.append(int(step.fb.rasterizer.last_num_rendered()))
+    finally:
+        _lib.profile_enable(False)
+    return {k: v / steps for k, v in acc.items()}, sum(Rs) / len(Rs)
+
+
+def cpu_baseline(wl, step, sample_cam=0):
+    """One full frame (fwd+bwd) of the same workload on the host through the C oracle (1 thread)."""
+    from oracle import cpu
+    import numpy as np
+    cam = wl["cams"][sample_cam]
+    rs = step.settings(cam)
+    A = {k: v.detach().cpu().numpy() for k, v in wl["attrs"].items()}
+    vis = None
+    if wl["face_visible"] is not None:
+        vis = wl["face_visible"][sample_cam].bool()[wl["mesh"]["cells"]].cpu().numpy().astype(np.uint8)
+    cot = wl["cot_host"][sample_cam].numpy()
+    t = time.perf_counter()
+    f = cpu.forward(rs, A["means3D"], A["opacities"], shs=A["shs"], scales=A["scales"], rots=A["rotations"],
+                    visibility=vis)
+    cpu.backward(rs, f, A["means3D"], cot, shs=A["shs"], scales=A["scales"], rots=A["rotations"])
+    dt = time.perf_counter() - t
+    return dict(value=1.0 / dt, unit=UNIT, cores=1, kind="port",
+                sample=f"1 full frame (fwd+bwd) of the same workload, camera {sample_cam}, oracle/raster_oracle.c, "
+                       f"single thread, {dt:.1f} s"), f["binned"]["num_rendered"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0:
+        log(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: using WORLD_SIZE")
+
+    if args.impl == "reference":
+        from oracle import refdgr
+        if not refdgr.available():
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dgr_C.so not built (needs /root/reference)"}))
+            return
+
+    import frosting_b200 as fb
+    from frosting_b200 import _lib
+    wl = build_workload(args.workload, device, rank, world)
+    precompute_visibility(wl, device)
+    step = OursStep(wl, device) if args.impl == "ours" else ReferenceStep(wl, device)
+    log(f"[bench] rank {rank}: workload {args.workload} built in {wl['gen_s']:.1f}s, impl={args.impl}")
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    secs, t0, t1 = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=False)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches_timed = timed_loop.launches   # kernels of libfrosting_b200.so launched inside the timed region
+    value = world * args.steps / secs
+
+    secs_e2e, _, _ = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=True)
+    e2e_value = world * args.steps / secs_e2e
+    H, W, P = wl["H"], wl["W"], wl["P"]
+    h2d = 3 * H * W * 4 + (16 + 16 + 3 + 3) * 4
+    d2h = 4
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": {"c3": "C3: 2M frosting-layer Gaussians (mesh-bound prism cells, occlusion culling ON), "
+                               "1920x1080, SH degree 3", "c2": "C2: 500k random Gaussians 800x800 SH3",
+                         "c5": "C5: 6M random Gaussians 1600x1200 SH3", "tiny": "tiny smoke workload"}[args.workload],
+            "gaussians": P, "image": f"{W}x{H}", "sh_degree": wl["D"], "cameras_per_gpu": CAMS_PER_GPU,
+            "parallelism": f"camera-batch x{world} (Gaussians replicated, NCCL all-reduce of the scalar loss)",
+            "frame": "occlusion mask + rasterizer forward + (color*G).sum() + backward to all attributes",
+            "l2": "inputs larger than L2: ~236 B x P of attributes read per frame, no flush needed",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "per step: cotangent image + camera tensors copied from pinned host memory on a copy "
+                        "stream, loss read back with .item(); model parameters stay resident as in the reference"},
+        "gpu_launches": launches_timed,
+    }
+    if clocks:
+        out["clocks"] = clocks
+    if args.impl == "reference":
+        out["impl"] = "reference"
+        out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                               "sample": "the reference's own CUDA rasterizer (oracle/_ref, built from /root/reference) "
+                                         "on the GPU: the reference has no CPU implementation of this path"}
+    else:
+        try:
+            prof, R_avg = stage_profile(step, wl, device, min(args.steps, 16))
+            peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(pk):
+                peaks = {"hbm_gbs": float(json.load(open(pk))["hbm_gbs"]), "src": "measured"}
+            T = ((W + 15) // 16) * ((H + 15) // 16)
+            Npx = H * W
+            b_fwd = 40 * R_avg + 20 * Npx + 8 * T + 12
+            b_bwd = 76 * R_avg + 20 * Npx + 8 * T + 12
+            traffic = {}
+            tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get(args.workload, {})
+
+            def roof(bytes_, ms, key):
+                ach = bytes_ / (ms * 1e-3) / 1e9
+                return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(key), "kernel": key,
+                        "kernel_ms": ms, "algorithmic_bytes": bytes_, "peak_source": peaks["src"],
+                        "instances_R": R_avg}
+            out["roofline"] = roof(b_bwd, prof["render_bwd"], "render_bwd_kernel")
+            out["roofline_fwd"] = roof(b_fwd, prof["render_fwd"], "render_fwd_kernel")
+            out["stage_ms"] = prof
+        except Exception as ex:   # measurement must not take the headline down with it
+            out["roofline_error"] = repr(ex)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"], _ = cpu_baseline(wl, step)
+            except Exception as ex:
+                out["cpu_baseline_error"] = repr(ex)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

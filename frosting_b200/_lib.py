@@ -18,7 +18,10 @@ EXPORTED = [
     "fb200_abi_version", "fb200_last_error", "fb200_geom_bytes", "fb200_image_bytes",
     "fb200_binning_bytes", "fb200_forward", "fb200_backward", "fb200_mark_visible",
     "fb200_mesh_visibility", "fb200_gaussian_mask_from_faces", "fb200_get_layout",
+    "fb200_profile_enable", "fb200_profile_read", "fb200_kernel_launches",
 ]
+NUM_STAGES = 5
+STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
 
 
 class Params(C.Structure):
@@ -97,6 +100,11 @@ def lib():
     L.fb200_gaussian_mask_from_faces.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                                  C.c_void_p, C.c_void_p]
     L.fb200_get_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Layout)]
+    L.fb200_profile_enable.argtypes = [C.c_int32]
+    L.fb200_profile_enable.restype = C.c_int
+    L.fb200_profile_read.argtypes = [C.POINTER(C.c_float)]
+    L.fb200_profile_read.restype = C.c_int
+    L.fb200_kernel_launches.restype = C.c_int64
     for n in ("fb200_forward", "fb200_backward", "fb200_mark_visible", "fb200_mesh_visibility",
               "fb200_gaussian_mask_from_faces", "fb200_get_layout"):
         getattr(L, n).restype = C.c_int
@@ -104,6 +112,21 @@ def lib():
         raise RuntimeError("frosting_b200: ABI version mismatch between header and library")
     _lib = L
     return L
+
+
+def profile_enable(on: bool):
+    check(lib().fb200_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """Device milliseconds per stage of the most recent forward/backward on this thread."""
+    buf = (C.c_float * NUM_STAGES)()
+    check(lib().fb200_profile_read(buf))
+    return {n: float(buf[i]) for i, n in enumerate(STAGES)}
+
+
+def kernel_launches() -> int:
+    return int(lib().fb200_kernel_launches())
 
 
 class Fb200Error(RuntimeError):

@@ -4,6 +4,8 @@
 // reference: argument checks, workspace carving, kernel sequencing.  Differences by design:
 // raw device pointers instead of torch tensors, an explicit stream, no allocation, no host
 // synchronisation unless `debug` is set.
+#include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 
@@ -70,13 +72,69 @@ int validate(const fb200_params* prm, const fb200_inputs* in, const fb200_worksp
     return FB200_OK;
 }
 
+// ---- measurement hooks -------------------------------------------------------------------------------
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_profile{0};
+// Process-wide (not thread-local): torch's autograd engine calls fb200_backward from its own thread.
+struct StageEvents {
+    cudaEvent_t ev[FB200_NUM_STAGES][2];
+    bool made = false;
+    bool recorded[FB200_NUM_STAGES] = {};
+};
+StageEvents g_ev;
+std::mutex g_ev_mu;
+
+struct StageTimer {
+    int stage;
+    cudaStream_t s;
+    bool on;
+    StageTimer(int st, cudaStream_t stream) : stage(st), s(stream), on(g_profile.load() != 0) {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_ev_mu);
+        if (!g_ev.made) {
+            for (int i = 0; i < FB200_NUM_STAGES; ++i) { cudaEventCreate(&g_ev.ev[i][0]); cudaEventCreate(&g_ev.ev[i][1]); }
+            g_ev.made = true;
+        }
+        cudaEventRecord(g_ev.ev[stage][0], s);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_ev_mu);
+        cudaEventRecord(g_ev.ev[stage][1], s);
+        g_ev.recorded[stage] = true;
+    }
+};
+
 inline char* align128(void* p) {
     return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
 }
 
 }  // namespace
 
+namespace fb200 {
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace fb200
+
 extern "C" {
+
+int fb200_profile_enable(int32_t enable) { g_profile.store(enable ? 1 : 0); return FB200_OK; }
+
+int fb200_profile_read(float* ms_out) {
+    if (!ms_out) return fail(FB200_EINVAL, "profile_read: null output%s");
+    std::lock_guard<std::mutex> lk(g_ev_mu);
+    for (int i = 0; i < FB200_NUM_STAGES; ++i) {
+        ms_out[i] = -1.0f;
+        if (g_ev.made && g_ev.recorded[i]) {
+            cudaError_t e = cudaEventSynchronize(g_ev.ev[i][1]);
+            if (e != cudaSuccess) return check(e, "profile_read");
+            e = cudaEventElapsedTime(&ms_out[i], g_ev.ev[i][0], g_ev.ev[i][1]);
+            if (e != cudaSuccess) return check(e, "profile_read");
+        }
+    }
+    return FB200_OK;
+}
+
+int64_t fb200_kernel_launches(void) { return g_launches.load(); }
 
 int fb200_abi_version(void) { return FB200_ABI_VERSION; }
 const char* fb200_last_error(void) { return g_err; }
@@ -141,9 +199,12 @@ int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_w
     a.out_color = d_out_color;
     a.radii = d_radii;
 
-    if ((rc = stage(launch_preprocess_fwd(a, s), "preprocess", debug, s)) != FB200_OK) return rc;
-    if ((rc = stage(launch_binning(a, s), "binning", debug, s)) != FB200_OK) return rc;
-    if ((rc = stage(launch_render_fwd(a, s), "render", debug, s)) != FB200_OK) return rc;
+    { StageTimer t(FB200_STAGE_PREPROCESS, s);
+      if ((rc = stage(launch_preprocess_fwd(a, s), "preprocess", debug, s)) != FB200_OK) return rc; }
+    { StageTimer t(FB200_STAGE_BINNING, s);
+      if ((rc = stage(launch_binning(a, s), "binning", debug, s)) != FB200_OK) return rc; }
+    { StageTimer t(FB200_STAGE_RENDER_FWD, s);
+      if ((rc = stage(launch_render_fwd(a, s), "render", debug, s)) != FB200_OK) return rc; }
     return FB200_OK;
 }
 
@@ -186,8 +247,11 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     a.dL_dpix = d_dL_dout_color;
     a.g = *grads;
 
-    if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc;
-    if ((rc = stage(launch_geom_bwd(a, s), "geometry backward", debug, s)) != FB200_OK) return rc;
+    if ((rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
+    { StageTimer t(FB200_STAGE_RENDER_BWD, s);
+      if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc; }
+    { StageTimer t(FB200_STAGE_GEOM_BWD, s);
+      if ((rc = stage(launch_geom_bwd(a, s), "geometry backward", debug, s)) != FB200_OK) return rc; }
     return FB200_OK;
 }
 

@@ -321,10 +321,14 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
     tile_scan_kernel<<<1, 1024, 0, s>>>(T, a.tile_count, a.ranges, a.cursor, a.list_small, a.list_large,
                                         a.list_huge, a.counters, a.capacity, a.status);
-    if (a.prm.P > 0)
+    count_launch();
+    if (a.prm.P > 0) {
         scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a.prm.P, a.tiles_x, a.rect, a.depth, a.cursor,
                                                              a.keys, a.status);
+        count_launch();
+    }
     single_instance_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, a.ranges, a.keys, a.point_list, a.status);
+    count_launch(3);   // + the two sort kernels below
     // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides
     // over its list.
     {

@@ -298,7 +298,7 @@ geom_bwd_kernel(BwdArgs a) {
 }  // namespace
 
 cudaError_t launch_geom_bwd(const BwdArgs& a, cudaStream_t s) {
-    if (a.prm.P > 0) geom_bwd_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a);
+    if (a.prm.P > 0) { geom_bwd_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a); count_launch(); }
     return cudaGetLastError();
 }
 

@@ -23,19 +23,21 @@ typedef unsigned long long u64;
 
 struct ClipV { float x, y, z, w; };
 
+// All arithmetic below uses explicit round-to-nearest intrinsics (no compiler-chosen FMA contraction) so
+// that oracle/raster_oracle.c reproduces every coverage decision bit for bit.
 __device__ __forceinline__ ClipV to_clip(const float* __restrict__ m, float x, float y, float z) {
     ClipV c;
-    c.x = m[0] * x + m[4] * y + m[8] * z + m[12];
-    c.y = m[1] * x + m[5] * y + m[9] * z + m[13];
-    c.z = m[2] * x + m[6] * y + m[10] * z + m[14];
-    c.w = m[3] * x + m[7] * y + m[11] * z + m[15];
+    c.x = affine_row(m, 0, x, y, z);
+    c.y = affine_row(m, 1, x, y, z);
+    c.z = affine_row(m, 2, x, y, z);
+    c.w = affine_row(m, 3, x, y, z);
     return c;
 }
 
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return ffma(fadd(b, -a), t, a); }
 __device__ __forceinline__ ClipV lerp(const ClipV& a, const ClipV& b, float t) {
     ClipV c;
-    c.x = a.x + (b.x - a.x) * t; c.y = a.y + (b.y - a.y) * t;
-    c.z = a.z + (b.z - a.z) * t; c.w = a.w + (b.w - a.w) * t;
+    c.x = lerp1(a.x, b.x, t); c.y = lerp1(a.y, b.y, t); c.z = lerp1(a.z, b.z, t); c.w = lerp1(a.w, b.w, t);
     return c;
 }
 
@@ -47,7 +49,7 @@ __device__ __forceinline__ float edge_fn(const ScreenV& a, const ScreenV& b, flo
     const bool swap = (a.x > b.x) || (a.x == b.x && a.y > b.y);
     const ScreenV& p = swap ? b : a;
     const ScreenV& q = swap ? a : b;
-    const float e = (q.x - p.x) * (py - p.y) - (q.y - p.y) * (px - p.x);
+    const float e = fadd(fmul(fadd(q.x, -p.x), fadd(py, -p.y)), -fmul(fadd(q.y, -p.y), fadd(px, -p.x)));
     return swap ? -e : e;
 }
 
@@ -56,7 +58,7 @@ __device__ __forceinline__ float edge_fn(const ScreenV& a, const ScreenV& b, flo
 // the interior at larger x has dy < 0 ("left").  A shared edge is traversed in opposite directions by
 // its two triangles, so exactly one of them owns the pixels lying exactly on it.
 __device__ __forceinline__ bool is_top_left(const ScreenV& a, const ScreenV& b) {
-    const float dx = b.x - a.x, dy = b.y - a.y;
+    const float dx = fadd(b.x, -a.x), dy = fadd(b.y, -a.y);
     return (dy == 0.f && dx > 0.f) || (dy < 0.f);
 }
 
@@ -79,10 +81,10 @@ __device__ void raster_triangle(ScreenV v0, ScreenV v1, ScreenV v2, int W, int H
     const long long barea = (long long)bw * bh;
     if (barea <= area_lo || barea > area_hi) return;
     const bool tl0 = is_top_left(v1, v2), tl1 = is_top_left(v2, v0), tl2 = is_top_left(v0, v1);
-    const float inv_area = 1.0f / area;
+    const float inv_area = __frcp_rn(area);
     for (long long k = lane; k < barea; k += kGroup) {
         const int px = x0 + (int)(k % bw), py = y0 + (int)(k / bw);
-        const float cx = px + 0.5f, cy = py + 0.5f;
+        const float cx = fadd((float)px, 0.5f), cy = fadd((float)py, 0.5f);
         const float w0 = edge_fn(v1, v2, cx, cy);
         const float w1 = edge_fn(v2, v0, cx, cy);
         const float w2 = edge_fn(v0, v1, cx, cy);
@@ -90,7 +92,7 @@ __device__ void raster_triangle(ScreenV v0, ScreenV v1, ScreenV v2, int W, int H
         const bool in1 = w1 > 0.f || (w1 == 0.f && tl1);
         const bool in2 = w2 > 0.f || (w2 == 0.f && tl2);
         if (!(in0 && in1 && in2)) continue;
-        const float z = (w0 * v0.z + w1 * v1.z + w2 * v2.z) * inv_area;
+        const float z = fmul(fadd(fadd(fmul(w0, v0.z), fmul(w1, v1.z)), fmul(w2, v2.z)), inv_area);
         if (!(z >= 0.f && z <= 1.f)) continue;   // per-fragment near/far clip (-w <= z_clip <= w)
         const u64 key = ((u64)__float_as_uint(z) << 32) | (uint32_t)face;
         atomicMin(zbuf + (size_t)py * W + px, key);
@@ -98,11 +100,11 @@ __device__ void raster_triangle(ScreenV v0, ScreenV v1, ScreenV v2, int W, int H
 }
 
 __device__ __forceinline__ ScreenV to_screen(const ClipV& c, int W, int H) {
-    const float iw = 1.0f / c.w;
+    const float iw = __frcp_rn(c.w);
     ScreenV s;
-    s.x = (c.x * iw * 0.5f + 0.5f) * W;
-    s.y = (c.y * iw * 0.5f + 0.5f) * H;
-    s.z = c.z * iw * 0.5f + 0.5f;
+    s.x = fmul(fadd(fmul(fmul(c.x, iw), 0.5f), 0.5f), (float)W);
+    s.y = fmul(fadd(fmul(fmul(c.y, iw), 0.5f), 0.5f), (float)H);
+    s.z = fadd(fmul(fmul(c.z, iw), 0.5f), 0.5f);
     return s;
 }
 
@@ -124,7 +126,7 @@ raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __res
     c[1] = to_clip(m, verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
     c[2] = to_clip(m, verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]);
     // near plane of the GL clip volume: z + w >= 0 (implies w > 0 for any sane projection)
-    const float d0 = c[0].z + c[0].w, d1 = c[1].z + c[1].w, d2 = c[2].z + c[2].w;
+    const float d0 = fadd(c[0].z, c[0].w), d1 = fadd(c[1].z, c[1].w), d2 = fadd(c[2].z, c[2].w);
     const bool in0 = d0 >= 0.f && c[0].w > 1e-12f, in1 = d1 >= 0.f && c[1].w > 1e-12f, in2 = d2 >= 0.f && c[2].w > 1e-12f;
     const int nin = (int)in0 + (int)in1 + (int)in2;
     if (nin == 0) return;
@@ -142,7 +144,7 @@ raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __res
         const int a = e, b = (e + 1) % 3;
         if (in[a]) poly[np++] = c[a];
         if (in[a] != in[b]) {
-            const float t = d[a] / (d[a] - d[b]);
+            const float t = __fdiv_rn(d[a], fadd(d[a], -d[b]));
             ClipV p = lerp(c[a], c[b], t);
             if (!(p.w > 1e-12f)) p.w = 1e-12f;
             poly[np++] = p;
@@ -217,6 +219,8 @@ cudaError_t launch_mesh_visibility(int V, int F, const float* verts, const int32
                 F, verts, faces, proj, W, H, kMid, 0x7fffffff, zbuf);
         }
     }
+    if (F > 0) count_launch(3);
+    if (N > 0) count_launch();
     if (N > 0)
         resolve_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>((int)N, F, zbuf, pix_to_face, face_visible,
                                                                    mark_last_on_bg);
@@ -226,7 +230,7 @@ cudaError_t launch_mesh_visibility(int V, int F, const float* verts, const int32
 cudaError_t launch_mask_from_faces(int n_points, const long long* cells, int F, const uint8_t* face_visible,
                                    int n_bg, uint8_t* mask, cudaStream_t s) {
     const int n = n_points + n_bg;
-    if (n > 0) mask_from_faces_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_points, cells, F, face_visible, n_bg, mask);
+    if (n > 0) { mask_from_faces_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_points, cells, F, face_visible, n_bg, mask); count_launch(); }
     return cudaGetLastError();
 }
 

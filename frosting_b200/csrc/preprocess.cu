@@ -369,12 +369,13 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a, cudaStream_t s) {
     if (a.prm.P > 0) {
         const int blocks = (a.prm.P + 255) / 256;
         preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(a);
+        count_launch();
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s) {
-    if (P > 0) mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, present);
+    if (P > 0) { mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, present); count_launch(); }
     return cudaGetLastError();
 }
 

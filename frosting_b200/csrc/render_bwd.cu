@@ -221,10 +221,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
 }  // namespace
 
+cudaError_t launch_render_bwd_clear(const BwdArgs& a, cudaStream_t s) {
+    return cudaMemsetAsync(a.acc, 0, sizeof(float) * 12 * (size_t)a.prm.P, s);
+}
+
 cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
-    cudaError_t e = cudaMemsetAsync(a.acc, 0, sizeof(float) * 12 * (size_t)a.prm.P, s);
-    if (e != cudaSuccess) return e;
+    count_launch();
     render_bwd_kernel<<<T, 256, 0, s>>>(a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height,
                                         a.tiles_x, a.in.d_background, a.final_T, a.n_contrib, a.dL_dpix, a.acc,
                                         a.status);

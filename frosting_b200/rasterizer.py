@@ -42,6 +42,7 @@ class GaussianRasterizationSettings(NamedTuple):
 # frame and the forward is re-run if the device-side overflow flag comes back set (the reference
 # instead stalls the pipeline on a D2H copy between preprocess and binning).
 _capacity_hint = {}
+_last = {"num_rendered": 0}
 NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove it is output-neutral
 
 
@@ -147,6 +148,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
                 break
             capacity = int(num_rendered * 1.05) + 1024     # exact count known now: one retry suffices
         _capacity_hint[key] = int(num_rendered * 1.125) + 4096
+        _last["num_rendered"] = num_rendered
 
     call = _Call()
     call.prm, call.inp, call.ws = prm, inp, ws
@@ -186,6 +188,11 @@ def _launch_backward(call: "_Call", radii, grad_out_color):
                                     C.c_void_p(g.data_ptr()), C.byref(grads),
                                     C.c_void_p(stream.cuda_stream)))
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def last_num_rendered() -> int:
+    """R (tile instances) of the most recent forward in this process."""
+    return _last["num_rendered"]
 
 
 def cpu_deep_copy_tuple(input_tuple):

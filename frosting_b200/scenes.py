@@ -154,7 +154,7 @@ def uv_sphere(n_lat, n_lon, radius=3.0, centre=(0.0, 0.0, 6.0)):
 
 
 def frosting_layer(P, cam, seed, n_faces_target=1_000_000, device="cpu", sh_coeffs=16, thickness=0.02,
-                   n_min_per_cell=1):
+                   n_min_per_cell=1, view_distance=7.5):
     """Frosting-layer scene: Gaussians bound to prism cells over a UV-sphere base mesh.
 
     Returns the *learnable parameters* (bary logits, opacity logits, log scales, raw quaternions, SH dc/rest)
@@ -184,7 +184,7 @@ def frosting_layer(P, cam, seed, n_faces_target=1_000_000, device="cpu", sh_coef
     bary = (u[:, 1:] - u[:, :-1]).clamp_min(1e-6)
     bary_logits = bary.log()
     fx = cam.image_width / (2 * cam.tanfovx)
-    s0 = 1.5 * 4.5 / fx
+    s0 = 1.5 * view_distance / fx     # median screen-space sigma ~1.5 px at the viewing distance
     log_scales = math.log(s0) + 0.5 * torch.randn(P, 3, generator=g)
     log_scales[:, 2] -= 1.0    # flatter along one axis, like surface-aligned splats
     quats = torch.randn(P, 4, generator=g)

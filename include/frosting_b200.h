@@ -167,6 +167,22 @@ typedef struct fb200_layout {
 int fb200_get_layout(int32_t P, int32_t image_width, int32_t image_height, int64_t capacity,
                      fb200_layout* out);
 
+/* Measurement hooks (bench.py's roofline block).  When enabled, every kernel stage of
+ * fb200_forward / fb200_backward is bracketed by cudaEvents on the caller's stream (the stream the
+ * kernels are launched on); fb200_profile_read() synchronises those events and returns the device
+ * time of each stage of the most recent forward/backward pair.  Off by default: no events are recorded
+ * and the hot path pays nothing. */
+#define FB200_STAGE_PREPROCESS 0
+#define FB200_STAGE_BINNING 1      /* tile scan + scatter + per-tile sort */
+#define FB200_STAGE_RENDER_FWD 2   /* alpha-blend forward kernel alone */
+#define FB200_STAGE_RENDER_BWD 3   /* alpha-blend backward kernel alone (accumulator memset excluded) */
+#define FB200_STAGE_GEOM_BWD 4
+#define FB200_NUM_STAGES 5
+int fb200_profile_enable(int32_t enable);
+int fb200_profile_read(float* ms_out /* [FB200_NUM_STAGES] */);
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t fb200_kernel_launches(void);
+
 const char* fb200_last_error(void);
 int fb200_abi_version(void);
 

@@ -531,7 +531,7 @@ static void raster_tri(sv_t v0, sv_t v1, sv_t v2, int W, int H, int face, uint64
             float cx = px + 0.5f, cy = py + 0.5f;
             float w0 = edge_fn(v1, v2, cx, cy), w1 = edge_fn(v2, v0, cx, cy), w2 = edge_fn(v0, v1, cx, cy);
             if (!((w0 > 0.f || (w0 == 0.f && tl0)) && (w1 > 0.f || (w1 == 0.f && tl1)) && (w2 > 0.f || (w2 == 0.f && tl2)))) continue;
-            float z = (w0 * v0.z + w1 * v1.z + w2 * v2.z) * inv_area;
+            float z = (((w0 * v0.z) + (w1 * v1.z)) + (w2 * v2.z)) * inv_area;
             if (!(z >= 0.f && z <= 1.f)) continue;
             uint64_t key = ((uint64_t)f2u(z) << 32) | (uint32_t)face;
             uint64_t* p = zbuf + (size_t)py * W + px;
@@ -542,7 +542,7 @@ static void raster_tri(sv_t v0, sv_t v1, sv_t v2, int W, int H, int face, uint64
 typedef struct { float x, y, z, w; } cv_t;
 static sv_t to_screen(cv_t c, int W, int H) {
     float iw = 1.0f / c.w; sv_t s;
-    s.x = (c.x * iw * 0.5f + 0.5f) * W; s.y = (c.y * iw * 0.5f + 0.5f) * H; s.z = c.z * iw * 0.5f + 0.5f;
+    s.x = (((c.x * iw) * 0.5f) + 0.5f) * (float)W; s.y = (((c.y * iw) * 0.5f) + 0.5f) * (float)H; s.z = ((c.z * iw) * 0.5f) + 0.5f;
     return s;
 }
 
@@ -556,10 +556,10 @@ void oracle_mesh_raster(int V, int F, const float* verts, const int32_t* faces, 
         cv_t c[3];
         for (int k = 0; k < 3; ++k) {
             const float* p = verts + 3 * (size_t)faces[3 * f + k];
-            c[k].x = m[0] * p[0] + m[4] * p[1] + m[8] * p[2] + m[12];
-            c[k].y = m[1] * p[0] + m[5] * p[1] + m[9] * p[2] + m[13];
-            c[k].z = m[2] * p[0] + m[6] * p[1] + m[10] * p[2] + m[14];
-            c[k].w = m[3] * p[0] + m[7] * p[1] + m[11] * p[2] + m[15];
+            c[k].x = affine_row(m, 0, p[0], p[1], p[2]);
+            c[k].y = affine_row(m, 1, p[0], p[1], p[2]);
+            c[k].z = affine_row(m, 2, p[0], p[1], p[2]);
+            c[k].w = affine_row(m, 3, p[0], p[1], p[2]);
         }
         float d[3]; int in[3], nin = 0;
         for (int k = 0; k < 3; ++k) { d[k] = c[k].z + c[k].w; in[k] = d[k] >= 0.f && c[k].w > 1e-12f; nin += in[k]; }
@@ -572,8 +572,8 @@ void oracle_mesh_raster(int V, int F, const float* verts, const int32_t* faces, 
             if (in[a] != in[b]) {
                 float t = d[a] / (d[a] - d[b]);
                 cv_t p;
-                p.x = c[a].x + (c[b].x - c[a].x) * t; p.y = c[a].y + (c[b].y - c[a].y) * t;
-                p.z = c[a].z + (c[b].z - c[a].z) * t; p.w = c[a].w + (c[b].w - c[a].w) * t;
+                p.x = fmaf(c[b].x - c[a].x, t, c[a].x); p.y = fmaf(c[b].y - c[a].y, t, c[a].y);
+                p.z = fmaf(c[b].z - c[a].z, t, c[a].z); p.w = fmaf(c[b].w - c[a].w, t, c[a].w);
                 if (!(p.w > 1e-12f)) p.w = 1e-12f;
                 poly[np++] = p;
             }
