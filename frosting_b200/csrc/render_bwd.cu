@@ -1,4 +1,4 @@
-// render_bwd.cu -- backward of the alpha compositing, one CTA per 16x16 tile.
+// render_bwd.cu -- backward of the alpha compositing, one CTA per 16x16 tile, warp-autonomous.
 //
 // Replaces renderCUDA<3> backward (DGR/cuda_rasterizer/backward.cu:399-557): back-to-front
 // traversal from each pixel's last contributor, T recovered by division, gradients w.r.t. the
@@ -7,23 +7,23 @@
 //     cost).  Here a warp (8x4 pixels) reduces its 32 lanes' contributions with a transposing
 //     butterfly (14 shuffles for 9 values) and issues ONE red.global.add instruction per
 //     warp-Gaussian pair (9 active lanes, 9 addresses in one 48-byte accumulator record);
+//   * every warp walks the list on its own, 32 instances per step, starting at ITS deepest last
+//     contributor; no CTA barrier (v1 staged 256-instance batches cooperatively and was dominated by
+//     barrier stalls, profiles/r01_render_c3_v1_summary.json).  Records re-read by the 8 warps of a
+//     tile are L1/L2 hits;
 //   * the same conservative alpha>=1/255 extents as the forward kernel let a warp skip instances
-//     that cannot touch its sub-tile, plus everything behind the warp's deepest last contributor;
-//   * the traversal starts at the tile's deepest last contributor instead of the end of the list.
+//     that cannot touch its sub-tile.
 #include "common.cuh"
 
 namespace fb200 {
 
 namespace {
 
-constexpr int kBatch = 256;
-
-struct __align__(16) StageBufB {
-    float4 q0[kBatch];
-    float4 q1[kBatch];
-    float cb[kBatch];
-    uint32_t id[kBatch];
-    uint32_t words[kWarpsPerTile][kBatch / 32];
+struct __align__(16) WarpSlabB {
+    float4 q0[32];
+    float4 q1[32];
+    float cb[32];
+    uint32_t id[32];
 };
 
 __device__ __forceinline__ bool overlaps(float lo, float hi, float c, float ext) {
@@ -69,18 +69,21 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   const float* __restrict__ bg, const float* __restrict__ final_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
                   float* __restrict__ acc, const int32_t* __restrict__ status) {
-    __shared__ StageBufB sb[2];
-    __shared__ uint32_t s_wmax[kWarpsPerTile];
+    __shared__ WarpSlabB slabs[kWarpsPerTile];
     if (status[FB200_ST_OVERFLOW]) return;
 
+    const unsigned full = 0xffffffffu;
     const int tile = blockIdx.x;
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSlabB& slab = slabs[warp];
     const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
     const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
     const int pix_x = sub_x0 + (lane & 7), pix_y = sub_y0 + (lane >> 3);
     const bool inside = pix_x < W && pix_y < H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float lox = (float)sub_x0, hix = (float)(sub_x0 + kSubW - 1);
+    const float loy = (float)sub_y0, hiy = (float)(sub_y0 + kSubH - 1);
     const size_t pix_id = (size_t)pix_y * W + pix_x;
     const size_t HW = (size_t)H * W;
 
@@ -97,125 +100,96 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     const float bg_dot_dpixel = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    // deepest last contributor of the warp / of the tile
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
-    if (lane == 0) s_wmax[warp] = wmax;
-    __syncthreads();
-    uint32_t n_eff = 0;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerTile; ++w) n_eff = max(n_eff, s_wmax[w]);
-    const int n = (int)n_eff;   // positions [0, n) of the tile list matter
+    // positions [0, n) of the tile list matter to this warp
+    const int n = (int)__reduce_max_sync(full, last_contributor);
     if (n == 0) return;
-    const int n_batches = (n + kBatch - 1) / kBatch;
-
-    const float tx0 = (float)(tile_x * kTile), ty0 = (float)(tile_y * kTile);
 
     float T = T_final;
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;      // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;      // last_color
     float last_alpha = 0.f;
 
-    // software pipeline: batch k stages positions p = n-1-(k*256+tid), descending
-    uint32_t idx_next = 0, idx_next2 = 0;
+    // software pipeline: step s handles positions p = n-1-(s*32+lane), descending
+    uint32_t id_cur = 0, id_next = 0;
     float4 r0, r1, r2;
     r0 = r1 = r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < n) idx_next = point_list[range.x + (n - 1 - tid)];
-    if (kBatch + tid < n) idx_next2 = point_list[range.x + (n - 1 - kBatch - tid)];
-    if (tid < n) {
-        const float4* p = reinterpret_cast<const float4*>(rec + idx_next);
+    if (lane < n) {
+        id_cur = point_list[range.x + (n - 1 - lane)];
+        const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
         r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
     }
+    if (32 + lane < n) id_next = point_list[range.x + (n - 1 - 32 - lane)];
 
-    for (int b = 0; b < n_batches; ++b) {
-        StageBufB& s = sb[b & 1];
-        const int base = b * kBatch;
-        const int valid = min(kBatch, n - base);
-        {
-            const bool have = tid < valid;
-            const uint32_t pos = (uint32_t)(n - 1 - base - tid);   // list position of my instance
-            s.q0[tid] = r0;
-            s.q1[tid] = r1;
-            s.cb[tid] = r2.x;
-            s.id[tid] = idx_next;
-            const float cx = r0.x, cy = r0.y, ex = r2.y, ey = r2.z;
+    for (int base = 0; base < n; base += 32) {
+        const bool hit = (base + lane < n) && overlaps(lox, hix, r0.x, r2.y) && overlaps(loy, hiy, r0.y, r2.z);
+        uint32_t bits = __ballot_sync(full, hit);
+        if (hit) {
+            slab.q0[lane] = r0;
+            slab.q1[lane] = r1;
+            slab.cb[lane] = r2.x;
+            slab.id[lane] = id_cur;
+        }
+        id_cur = id_next;
+        if (base + 32 + lane < n) {
+            const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
+            r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+        }
+        if (base + 64 + lane < n) id_next = point_list[range.x + (n - 1 - base - 64 - lane)];
+        __syncwarp();
+
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t pos = (uint32_t)(n - 1 - base - j);
+            const float4 q0 = slab.q0[j];
+            const float4 q1 = slab.q1[j];
+            const float dx = fadd(q0.x, -pxf), dy = fadd(q0.y, -pyf);
+            const float q = ffma(dx, fmul(dx, q0.z), fmul(dy, fmul(dy, q1.x)));
+            const float u = fmul(dy, fmul(dx, q0.w));
+            const float power = ffma(q, -0.5f, -u);
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, fmul(q1.y, G));
+            const bool active = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (!__any_sync(full, active)) continue;
+
+            float v[8];
+            float v8 = 0.f;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerTile; ++w) {
-                const float lox = tx0 + (float)((w & 1) * kSubW), loy = ty0 + (float)((w >> 1) * kSubH);
-                const bool hit = have && pos < s_wmax[w] &&
-                                 overlaps(lox, lox + (float)(kSubW - 1), cx, ex) &&
-                                 overlaps(loy, loy + (float)(kSubH - 1), cy, ey);
-                const uint32_t word = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) s.words[w][warp] = word;
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            if (active) {
+                const float cb = slab.cb[j];
+                const float inv = __frcp_rn(1.f - alpha);    // T/(1-a) and T_final/(1-a) share one reciprocal
+                T = T * inv;
+                const float dchannel_dcolor = alpha * T;
+                ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0;
+                ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1;
+                ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2;
+                lc0 = q1.z; lc1 = q1.w; lc2 = cb;
+                float dL_dalpha = (q1.z - ar0) * dp0 + (q1.w - ar1) * dp1 + (cb - ar2) * dp2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final * inv) * bg_dot_dpixel;
+                const float dL_dG = q1.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
+                const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;       // dL/dmean2D.x
+                v[1] = dL_dG * dG_ddely * ddely_dy;       // dL/dmean2D.y
+                v[2] = -0.5f * gdx * dx * dL_dG;          // dL/dconic.x
+                v[3] = -0.5f * gdx * dy * dL_dG;          // dL/dconic.y
+                v[4] = -0.5f * gdy * dy * dL_dG;          // dL/dconic.w
+                v[5] = G * dL_dalpha;                     // dL/dopacity
+                v[6] = dchannel_dcolor * dp0;             // dL/dcolour
+                v[7] = dchannel_dcolor * dp1;
+                v8 = dchannel_dcolor * dp2;
             }
+            const float red = warp_reduce9(v, v8, lane);
+            // lane 4k holds value k (k = 0..7), lane 1 holds value 8
+            const int slot = (lane == 1) ? 8 : (lane >> 2);
+            if ((lane & 3) == 0 || lane == 1)
+                atomicAdd(acc + (size_t)slab.id[j] * 12 + slot, red);
         }
-        {
-            const int nb1 = base + kBatch + tid;
-            idx_next = idx_next2;
-            if (nb1 < n) {
-                const float4* p = reinterpret_cast<const float4*>(rec + idx_next);
-                r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
-            }
-            const int nb2 = nb1 + kBatch;
-            if (nb2 < n) idx_next2 = point_list[range.x + (n - 1 - nb2)];
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int c = 0; c < kBatch / 32; ++c) {
-            uint32_t bits = s.words[warp][c];
-            while (bits) {
-                const int j = c * 32 + (__ffs(bits) - 1);
-                bits &= bits - 1;
-                const uint32_t pos = (uint32_t)(n - 1 - base - j);
-                const float4 q0 = s.q0[j];
-                const float4 q1 = s.q1[j];
-                const float dx = fadd(q0.x, -pxf), dy = fadd(q0.y, -pyf);
-                const float q = ffma(dx, fmul(dx, q0.z), fmul(dy, fmul(dy, q1.x)));
-                const float u = fmul(dy, fmul(dx, q0.w));
-                const float power = ffma(q, -0.5f, -u);
-                const float G = expf(power);
-                const float alpha = fminf(0.99f, fmul(q1.y, G));
-                const bool active = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                if (!__any_sync(0xffffffffu, active)) continue;
-
-                float v[8];
-                float v8 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                if (active) {
-                    const float cb = s.cb[j];
-                    const float one_m_alpha = 1.f - alpha;
-                    T = T / one_m_alpha;
-                    const float dchannel_dcolor = alpha * T;
-                    ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0;
-                    ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1;
-                    ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2;
-                    lc0 = q1.z; lc1 = q1.w; lc2 = cb;
-                    float dL_dalpha = (q1.z - ar0) * dp0 + (q1.w - ar1) * dp1 + (cb - ar2) * dp2;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / one_m_alpha) * bg_dot_dpixel;
-                    const float dL_dG = q1.y * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-                    const float dG_ddely = -gdy * q1.x - gdx * q0.w;
-                    v[0] = dL_dG * dG_ddelx * ddelx_dx;       // dL/dmean2D.x
-                    v[1] = dL_dG * dG_ddely * ddely_dy;       // dL/dmean2D.y
-                    v[2] = -0.5f * gdx * dx * dL_dG;          // dL/dconic.x
-                    v[3] = -0.5f * gdx * dy * dL_dG;          // dL/dconic.y
-                    v[4] = -0.5f * gdy * dy * dL_dG;          // dL/dconic.w
-                    v[5] = G * dL_dalpha;                     // dL/dopacity
-                    v[6] = dchannel_dcolor * dp0;             // dL/dcolour
-                    v[7] = dchannel_dcolor * dp1;
-                    v8 = dchannel_dcolor * dp2;
-                }
-                const float red = warp_reduce9(v, v8, lane);
-                // lane 4k holds value k (k = 0..7), lane 1 holds value 8
-                const int slot = (lane == 1) ? 8 : (lane >> 2);
-                if ((lane & 3) == 0 || lane == 1)
-                    atomicAdd(acc + (size_t)s.id[j] * 12 + slot, red);
-            }
-        }
+        __syncwarp();   // slab is rewritten by the next step
     }
 }
 
