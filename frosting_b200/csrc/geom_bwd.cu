@@ -41,9 +41,19 @@ __device__ __forceinline__ V3 symv(const float* c, V3 t) {
               c[2] * t.x + c[4] * t.y + c[5] * t.z);
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kGeomThreads = 128;
+constexpr int kShRow = 13;   // float4 per staged SH-gradient row: 12 + 1 pad => conflict-free 128-bit accesses
+
+// coalesced zero fill of `n4` float4 starting at a 16-byte aligned address, by one warp
+__device__ __forceinline__ void warp_zero4(float* base, int n4, int lane) {
+    float4* p = reinterpret_cast<float4*>(base);
+    for (int i = lane; i < n4; i += 32) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(kGeomThreads)
 geom_bwd_kernel(BwdArgs a) {
     __shared__ float view[16], proj[16], campos[3];
+    __shared__ float4 sh_stage[kGeomThreads / 32][32 * kShRow];
     if (threadIdx.x < 16) {
         view[threadIdx.x] = a.in.d_viewmatrix[threadIdx.x];
         proj[threadIdx.x] = a.in.d_projmatrix[threadIdx.x];
@@ -53,10 +63,33 @@ geom_bwd_kernel(BwdArgs a) {
 
     const int P = a.prm.P, M = a.prm.sh_coeffs, D = a.prm.sh_degree;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const size_t i = (size_t)idx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g0 = idx - lane;                       // first Gaussian of this warp
+    const bool full_warp = g0 + 31 < P;              // all 32 lanes own a Gaussian
+    const bool in_range = idx < P;
+    const bool visible = in_range && a.radii[idx] > 0;
 
-    const bool visible = a.radii[idx] > 0;
+    // Warps whose 32 Gaussians are all invisible (culled / masked by occlusion: the common case for a
+    // Frosting layer, where visibility is coherent in face order) only have zeros to write: do it with
+    // fully coalesced 128-bit stores instead of 32 scattered scalar stores per thread.
+    if (full_warp && !__any_sync(0xffffffffu, visible)) {
+        const size_t g = (size_t)g0;
+        warp_zero4(a.g.d_dL_dmeans2D + 3 * g, 24, lane);
+        warp_zero4(a.g.d_dL_dcolors + 3 * g, 24, lane);
+        warp_zero4(a.g.d_dL_dopacity + g, 8, lane);
+        warp_zero4(a.g.d_dL_dmeans3D + 3 * g, 24, lane);
+        warp_zero4(a.g.d_dL_dcov3D + 6 * g, 48, lane);
+        warp_zero4(a.g.d_dL_dscales + 3 * g, 24, lane);
+        warp_zero4(a.g.d_dL_drotations + 4 * g, 32, lane);
+        if (a.g.d_dL_dsh != nullptr && M > 0 && ((M * 3) & 3) == 0) warp_zero4(a.g.d_dL_dsh + (size_t)M * 3 * g, M * 24, lane);
+        else if (a.g.d_dL_dsh != nullptr && M > 0)
+            for (int k = lane; k < M * 3 * 32; k += 32) a.g.d_dL_dsh[(size_t)M * 3 * g + k] = 0.f;
+        return;
+    }
+    const size_t i = (size_t)(in_range ? idx : 0);
+    // SH gradients of a full warp are staged in shared memory and written out coalesced (M == 16)
+    const bool stage_sh = full_warp && M == 16 && a.g.d_dL_dsh != nullptr;
+    float4* stage = sh_stage[warp] + lane * kShRow;
 
     float g_mean2d_x = 0.f, g_mean2d_y = 0.f, g_op = 0.f;
     V3 g_col = v3(0.f, 0.f, 0.f), g_mean = v3(0.f, 0.f, 0.f);
@@ -218,7 +251,8 @@ geom_bwd_kernel(BwdArgs a) {
                             }
                         }
                     }
-                    dsh4[q] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (stage_sh) stage[q] = make_float4(o[0], o[1], o[2], o[3]);
+                    else dsh4[q] = make_float4(o[0], o[1], o[2], o[3]);
                 }
             } else {
                 for (int k = 0; k < M; ++k) {
@@ -276,15 +310,29 @@ geom_bwd_kernel(BwdArgs a) {
             g_rot.w = 2.f * qr * (Hm[0][1] - Hm[1][0]) + 2.f * qx * (Hm[2][0] + Hm[0][2]) + 2.f * qy * (Hm[1][2] + Hm[2][1]) - 4.f * qz * (Hm[1][1] + Hm[0][0]);
         }
     }
-    if ((!visible || !has_sh) && dsh != nullptr) {
+    if ((!visible || !has_sh) && dsh != nullptr && in_range) {
         if (M == 16) {
             float4* dsh4 = reinterpret_cast<float4*>(dsh);
 #pragma unroll
-            for (int q = 0; q < 12; ++q) dsh4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 12; ++q) {
+                if (stage_sh) stage[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else dsh4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         } else {
             for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
         }
     }
+    if (stage_sh) {
+        __syncwarp();
+        float4* out4 = reinterpret_cast<float4*>(a.g.d_dL_dsh + (size_t)48 * g0);
+        const float4* rows = sh_stage[warp];
+#pragma unroll
+        for (int r = 0; r < 12; ++r) {
+            const int f = r * 32 + lane;            // float4 index within the warp's 6 KB block
+            out4[f] = rows[(f / 12) * kShRow + (f % 12)];
+        }
+    }
+    if (!in_range) return;
 
     a.g.d_dL_dmeans2D[3 * i] = g_mean2d_x; a.g.d_dL_dmeans2D[3 * i + 1] = g_mean2d_y; a.g.d_dL_dmeans2D[3 * i + 2] = 0.f;
     a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z;
@@ -298,7 +346,10 @@ geom_bwd_kernel(BwdArgs a) {
 }  // namespace
 
 cudaError_t launch_geom_bwd(const BwdArgs& a, cudaStream_t s) {
-    if (a.prm.P > 0) { geom_bwd_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a); count_launch(); }
+    if (a.prm.P > 0) {
+        geom_bwd_kernel<<<(a.prm.P + kGeomThreads - 1) / kGeomThreads, kGeomThreads, 0, s>>>(a);
+        count_launch();
+    }
     return cudaGetLastError();
 }
 

@@ -30,11 +30,14 @@ __device__ __forceinline__ bool overlaps(float lo, float hi, float c, float ext)
     return !(c + ext < lo) && !(c - ext > hi);
 }
 
-// Sum each of v[0..7] and v8 over the 32 lanes.  On return lane 4*k (k=0..7) holds sum(v[k]) in
-// `out`, lane 1 holds sum(v8) in `out`.
-__device__ __forceinline__ float warp_reduce9(const float (&v)[8], float v8, int lane) {
+// Sum each of v[0..7] and v8 over the 32 lanes with 12 shuffles: a transposing butterfly halves the number
+// of live values at every step (8 -> 4 -> 2 -> 1) while the ninth value rides along and is folded into the
+// last transposing step.  On return lane 4k+{0,1} ... : lanes with (lane & 3) < 2 hold
+//   value index  (lane >> 2)            if (lane & 2) == 0   [k = 0..7]
+// and lanes with (lane & 2) != 0 hold value 8.  The caller uses lanes with (lane & 3) == 0 (values 0..7)
+// and lane 2 (value 8).
+__device__ __forceinline__ float warp_reduce9(const float (&v)[8], float v8, bool b4, bool b3, bool b2, bool b1) {
     const unsigned full = 0xffffffffu;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
     float w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -42,6 +45,7 @@ __device__ __forceinline__ float warp_reduce9(const float (&v)[8], float v8, int
         const float keep = b4 ? v[i + 4] : v[i];
         w[i] = keep + __shfl_xor_sync(full, send, 16);
     }
+    v8 += __shfl_xor_sync(full, v8, 16);
     float x[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -49,21 +53,27 @@ __device__ __forceinline__ float warp_reduce9(const float (&v)[8], float v8, int
         const float keep = b3 ? w[i + 2] : w[i];
         x[i] = keep + __shfl_xor_sync(full, send, 8);
     }
+    v8 += __shfl_xor_sync(full, v8, 8);
     float y;
     {
         const float send = b2 ? x[0] : x[1];
         const float keep = b2 ? x[1] : x[0];
         y = keep + __shfl_xor_sync(full, send, 4);
     }
-    y += __shfl_xor_sync(full, y, 2);
-    y += __shfl_xor_sync(full, y, 1);
-    // y on lane L = total of value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(full, v8, o);
-    return (lane == 1) ? v8 : y;
+    v8 += __shfl_xor_sync(full, v8, 4);
+    // y: value index (lane>>2)&7 summed over lane bits 4,3,2; v8 summed over the same bits.
+    // fold the pair (y, v8) over lane bit 1: lanes with bit1 = 0 keep y, lanes with bit1 = 1 keep v8
+    float z;
+    {
+        const float send = b1 ? y : v8;
+        const float keep = b1 ? v8 : y;
+        z = keep + __shfl_xor_sync(full, send, 2);
+    }
+    z += __shfl_xor_sync(full, z, 1);
+    return z;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                   const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
                   const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -75,7 +85,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     const unsigned full = 0xffffffffu;
     const int tile = blockIdx.x;
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int lane;
+    // volatile: keeps the lane id in a register (ptxas otherwise re-reads SR_TID.X inside the hot loop)
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const bool lb4 = lane & 16, lb3 = lane & 8, lb2 = lane & 4, lb1 = lane & 2;
+    const bool red_lane = ((lane & 3) == 0) || (lane == 2);
+    const int red_slot = (lane == 2) ? 8 : (lane >> 2);
     WarpSlabB& slab = slabs[warp];
     const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
     const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
@@ -183,11 +199,9 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                 v[7] = dchannel_dcolor * dp1;
                 v8 = dchannel_dcolor * dp2;
             }
-            const float red = warp_reduce9(v, v8, lane);
-            // lane 4k holds value k (k = 0..7), lane 1 holds value 8
-            const int slot = (lane == 1) ? 8 : (lane >> 2);
-            if ((lane & 3) == 0 || lane == 1)
-                atomicAdd(acc + (size_t)slab.id[j] * 12 + slot, red);
+            const float red = warp_reduce9(v, v8, lb4, lb3, lb2, lb1);
+            // lane 4k holds value k (k = 0..7), lane 2 holds value 8
+            if (red_lane) atomicAdd(acc + (size_t)slab.id[j] * 12 + red_slot, red);
         }
         __syncwarp();   // slab is rewritten by the next step
     }
