@@ -16,7 +16,7 @@ TILE = 16
 # every symbol include/frosting_b200.h declares
 EXPORTED = [
     "fb200_abi_version", "fb200_last_error", "fb200_geom_bytes", "fb200_image_bytes",
-    "fb200_binning_bytes", "fb200_forward", "fb200_backward", "fb200_mark_visible",
+    "fb200_binning_bytes", "fb200_forward", "fb200_forward_geometry", "fb200_forward_raster", "fb200_backward", "fb200_mark_visible",
     "fb200_mesh_visibility", "fb200_gaussian_mask_from_faces", "fb200_get_layout",
     "fb200_profile_enable", "fb200_profile_read", "fb200_kernel_launches",
 ]
@@ -91,6 +91,10 @@ def lib():
     L.fb200_binning_bytes.argtypes = [C.c_int64]
     L.fb200_forward.argtypes = [C.POINTER(Params), C.POINTER(Inputs), C.POINTER(Workspace),
                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fb200_forward_geometry.argtypes = [C.POINTER(Params), C.POINTER(Inputs), C.POINTER(Workspace),
+                                         C.c_void_p, C.c_void_p]
+    L.fb200_forward_raster.argtypes = [C.POINTER(Params), C.POINTER(Inputs), C.POINTER(Workspace),
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.fb200_backward.argtypes = [C.POINTER(Params), C.POINTER(Inputs), C.POINTER(Workspace),
                                  C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p]
     L.fb200_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -105,7 +109,7 @@ def lib():
     L.fb200_profile_read.argtypes = [C.POINTER(C.c_float)]
     L.fb200_profile_read.restype = C.c_int
     L.fb200_kernel_launches.restype = C.c_int64
-    for n in ("fb200_forward", "fb200_backward", "fb200_mark_visible", "fb200_mesh_visibility",
+    for n in ("fb200_forward", "fb200_forward_geometry", "fb200_forward_raster", "fb200_backward", "fb200_mark_visible", "fb200_mesh_visibility",
               "fb200_gaussian_mask_from_faces", "fb200_get_layout"):
         getattr(L, n).restype = C.c_int
     if L.fb200_abi_version() != 1:

@@ -68,7 +68,8 @@ int validate(const fb200_params* prm, const fb200_inputs* in, const fb200_worksp
     const BinLayout bl((size_t)ws->binning_capacity);
     if (ws->geom_bytes < gl.total) return fail(FB200_ENOSPC, "geometry workspace too small%s");
     if (ws->image_bytes < il.total) return fail(FB200_ENOSPC, "image workspace too small%s");
-    if (ws->binning_bytes < bl.total) return fail(FB200_ENOSPC, "binning workspace too small%s");
+    if (ws->binning_capacity > 0 && ws->binning_bytes < bl.total)
+        return fail(FB200_ENOSPC, "binning workspace too small%s");
     return FB200_OK;
 }
 
@@ -155,22 +156,18 @@ int fb200_get_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, fb200_la
     return FB200_OK;
 }
 
-int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
-                  float* d_out_color, int32_t* d_radii, void* stream) {
+static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws, bool need_binning,
+                     float* d_out_color, int32_t* d_radii, FwdArgs& a) {
     int rc = validate(prm, in, ws);
     if (rc != FB200_OK) return rc;
-    if (!d_out_color || (prm->P > 0 && !d_radii)) return fail(FB200_EINVAL, "output pointers missing%s");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool debug = (prm->debug & 1) != 0;
-
+    if (prm->P > 0 && !d_radii) return fail(FB200_EINVAL, "output pointers missing%s");
+    if (need_binning && !d_out_color) return fail(FB200_EINVAL, "output pointers missing%s");
     const GeomLayout gl((size_t)prm->P);
     const ImageLayout il(prm->image_width, prm->image_height);
     const BinLayout bl((size_t)ws->binning_capacity);
     char* g = align128(ws->d_geom);
     char* im = align128(ws->d_image);
     char* bn = ws->d_binning ? align128(ws->d_binning) : nullptr;
-
-    FwdArgs a;
     memset(&a, 0, sizeof(a));
     a.prm = *prm;
     a.in = *in;
@@ -198,14 +195,41 @@ int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_w
     a.status = ws->d_status;
     a.out_color = d_out_color;
     a.radii = d_radii;
+    return FB200_OK;
+}
 
+int fb200_forward_geometry(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                           int32_t* d_radii, void* stream) {
+    FwdArgs a;
+    int rc = setup_fwd(prm, in, ws, false, nullptr, d_radii, a);
+    if (rc != FB200_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool debug = (prm->debug & 1) != 0;
     { StageTimer t(FB200_STAGE_PREPROCESS, s);
-      if ((rc = stage(launch_preprocess_fwd(a, s), "preprocess", debug, s)) != FB200_OK) return rc; }
+      if ((rc = stage(launch_preprocess_fwd(a, s), "preprocess", debug, s)) != FB200_OK) return rc;
+      if ((rc = stage(launch_tile_scan(a, s), "tile scan", debug, s)) != FB200_OK) return rc; }
+    return FB200_OK;
+}
+
+int fb200_forward_raster(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                         float* d_out_color, int32_t* d_radii, void* stream) {
+    FwdArgs a;
+    int rc = setup_fwd(prm, in, ws, true, d_out_color, d_radii, a);
+    if (rc != FB200_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool debug = (prm->debug & 1) != 0;
     { StageTimer t(FB200_STAGE_BINNING, s);
       if ((rc = stage(launch_binning(a, s), "binning", debug, s)) != FB200_OK) return rc; }
     { StageTimer t(FB200_STAGE_RENDER_FWD, s);
       if ((rc = stage(launch_render_fwd(a, s), "render", debug, s)) != FB200_OK) return rc; }
     return FB200_OK;
+}
+
+int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                  float* d_out_color, int32_t* d_radii, void* stream) {
+    int rc = fb200_forward_geometry(prm, in, ws, d_radii, stream);
+    if (rc != FB200_OK) return rc;
+    return fb200_forward_raster(prm, in, ws, d_out_color, d_radii, stream);
 }
 
 int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,

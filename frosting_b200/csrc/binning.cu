@@ -317,10 +317,22 @@ single_instance_kernel(int T, const uint2* __restrict__ ranges, const u64* __res
 
 }  // namespace
 
-cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
+cudaError_t launch_tile_scan(const FwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
     tile_scan_kernel<<<1, 1024, 0, s>>>(T, a.tile_count, a.ranges, a.cursor, a.list_small, a.list_large,
                                         a.list_huge, a.counters, a.capacity, a.status);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// set the overflow word for a raster phase launched with its own capacity
+__global__ void check_capacity_kernel(long long capacity, int32_t* __restrict__ status) {
+    status[FB200_ST_OVERFLOW] = ((long long)status[FB200_ST_NUM_RENDERED] > capacity) ? 1 : 0;
+}
+
+cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
+    const int T = a.tiles_x * a.tiles_y;
+    check_capacity_kernel<<<1, 1, 0, s>>>(a.capacity, a.status);
     count_launch();
     if (a.prm.P > 0) {
         scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a.prm.P, a.tiles_x, a.rect, a.depth, a.cursor,

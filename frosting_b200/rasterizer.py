@@ -38,10 +38,6 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-# instance-capacity hint per device: the binning buffer is sized optimistically from the previous
-# frame and the forward is re-run if the device-side overflow flag comes back set (the reference
-# instead stalls the pipeline on a D2H copy between preprocess and binning).
-_capacity_hint = {}
 _last = {"num_rendered": 0}
 NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove it is output-neutral
 
@@ -129,25 +125,24 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
         status = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, device=device)
         status_host = _pinned_status(device)
 
-        key = (device.index, W, H)
-        capacity = max(int(_capacity_hint.get(key, 0)), 4 * P, 1024)
-        while True:
-            binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
-            ws = Workspace(d_geom=geom.data_ptr(), geom_bytes=geom.numel(),
-                           d_image=image.data_ptr(), image_bytes=image.numel(),
-                           d_binning=binning.data_ptr(), binning_bytes=binning.numel(),
-                           binning_capacity=capacity, d_status=status.data_ptr())
-            _lib.check(L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws),
-                                       C.c_void_p(out_color.data_ptr()),
-                                       C.c_void_p(radii.data_ptr()) if P > 0 else None,
-                                       C.c_void_p(stream.cuda_stream)))
-            status_host.copy_(status, non_blocking=True)
-            stream.synchronize()
-            num_rendered = int(status_host[_lib.ST_NUM_RENDERED])
-            if int(status_host[_lib.ST_OVERFLOW]) == 0:
-                break
-            capacity = int(num_rendered * 1.05) + 1024     # exact count known now: one retry suffices
-        _capacity_hint[key] = int(num_rendered * 1.125) + 4096
+        # Phase 1: preprocess + tile scan.  The exact instance count R comes back through a pinned
+        # mailbox; waiting for it covers ~0.1 ms of GPU work (the reference blocks at the same point,
+        # rasterizer_impl.cu:280-281).  Phase 2 is then launched with an exactly sized binning buffer and
+        # the caller's loss/backward launches queue up behind it while the GPU is busy.
+        ws = Workspace(d_geom=geom.data_ptr(), geom_bytes=geom.numel(),
+                       d_image=image.data_ptr(), image_bytes=image.numel(),
+                       d_binning=None, binning_bytes=0, binning_capacity=0, d_status=status.data_ptr())
+        rptr = C.c_void_p(radii.data_ptr()) if P > 0 else None
+        sptr = C.c_void_p(stream.cuda_stream)
+        _lib.check(L.fb200_forward_geometry(C.byref(prm), C.byref(inp), C.byref(ws), rptr, sptr))
+        status_host.copy_(status, non_blocking=True)
+        stream.synchronize()
+        num_rendered = int(status_host[_lib.ST_NUM_RENDERED])
+        capacity = max(num_rendered, 1)
+        binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
+        ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
+        _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
+                                          C.c_void_p(out_color.data_ptr()), rptr, sptr))
         _last["num_rendered"] = num_rendered
 
     call = _Call()

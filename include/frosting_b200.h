@@ -108,6 +108,17 @@ size_t fb200_binning_bytes(int64_t capacity);
 int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
                   float* d_out_color, int32_t* d_radii, void* stream);
 
+/* The same forward in two phases, for callers that want an exactly sized binning buffer and no retry:
+ *   fb200_forward_geometry : preprocess + per-tile counts + tile scan.  Needs only the geometry and image
+ *                            workspaces; writes d_radii and d_status[FB200_ST_NUM_RENDERED] (stream-ordered).
+ *   fb200_forward_raster   : scatter + per-tile sort + blend, with a binning buffer of capacity >= R.
+ * This is the reference's own split (it blocks on point_offsets[P-1] between preprocess and binning,
+ * rasterizer_impl.cu:280-284); here the wait is the caller's choice and covers ~0.1 ms of GPU work. */
+int fb200_forward_geometry(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                           int32_t* d_radii, void* stream);
+int fb200_forward_raster(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
+                         float* d_out_color, int32_t* d_radii, void* stream);
+
 /* Gradient outputs of the backward pass, shapes as DGR/rasterize_points.cu:151-159.
  * All are fully written by the call (invisible Gaussians get zeros); no pre-zeroing needed. */
 typedef struct fb200_grads {
