@@ -145,9 +145,25 @@ scatter_kernel(int P, int tiles_x, const uint2* __restrict__ rect, const float* 
 // is the same for every key is skipped), followed by a fix-up that orders runs of EQUAL depth by
 // Gaussian index -- together the total order (depth_bits, idx) of the reference's stable global sort.
 // Ranking is warp-synchronous: each warp owns a contiguous slice of the list, walks it 32 keys at a
-// time and ranks equal digits with __match_any_sync, so no per-key shared-memory atomics are needed.
+// time and ranks equal digits with ballots (digit_peers), so no per-key shared-memory atomics are needed.
 // kShared: ping-pong buffers in shared memory (lists up to kMaxN), else in global memory (L2) with a
 // caller-provided scratch array, for lists of any length.
+// Lanes holding the same 8-bit digit as this lane, among the lanes with `have` set: eight ballots and eight
+// LOP3s at fixed latency.  (__match_any_sync does the same in one instruction, but its latency grows with
+// the number of distinct values -- with 32 near-random digits it dominated this kernel: ~98 k cycles per
+// 1.5 k-key tile.)
+__device__ __forceinline__ unsigned digit_peers(uint32_t d, bool have) {
+    const unsigned full = 0xffffffffu;
+    unsigned peers = __ballot_sync(full, have);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(full, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 template <int kThreads>
 // NOTE: no __restrict__ on any of these pointers -- they are written by other threads of the CTA and
 // re-read after barriers; with __restrict__ nvcc forwards a thread's own stale store across
@@ -170,8 +186,8 @@ __device__ __forceinline__ void radix_sort_tile(u64* a, u64* b, int n,
         for (int i0 = seg_lo; i0 < seg_hi; i0 += 32) {
             const int i = i0 + lane;
             const bool have = i < seg_hi;
-            const uint32_t d = have ? (uint32_t)(src[i] >> shift) & 0xffu : 0x100u + lane;   // unique when idle
-            const unsigned peers = __match_any_sync(full, d);
+            const uint32_t d = have ? (uint32_t)(src[i] >> shift) & 0xffu : 0u;
+            const unsigned peers = digit_peers(d, have);
             if (have && (__ffs(peers) - 1) == lane) counters[warp * 256 + d] += __popc(peers);
             __syncwarp();
         }
@@ -215,8 +231,8 @@ __device__ __forceinline__ void radix_sort_tile(u64* a, u64* b, int n,
                 const int i = i0 + lane;
                 const bool have = i < seg_hi;
                 const u64 k = have ? src[i] : 0ull;
-                const uint32_t d = have ? (uint32_t)(k >> shift) & 0xffu : 0x100u + lane;
-                const unsigned peers = __match_any_sync(full, d);
+                const uint32_t d = have ? (uint32_t)(k >> shift) & 0xffu : 0u;
+                const unsigned peers = digit_peers(d, have);
                 uint32_t off = 0;
                 if (have) off = counters[warp * 256 + d] + __popc(peers & ((1u << lane) - 1u));
                 __syncwarp();
