@@ -19,6 +19,7 @@ EXPORTED = [
     "fb200_binning_bytes", "fb200_forward", "fb200_forward_geometry", "fb200_forward_raster", "fb200_backward", "fb200_mark_visible",
     "fb200_mesh_visibility", "fb200_gaussian_mask_from_faces", "fb200_get_layout",
     "fb200_profile_enable", "fb200_profile_read", "fb200_kernel_launches",
+    "fb200_frosting_attributes", "fb200_frosting_attributes_backward",
 ]
 NUM_STAGES = 5
 STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
@@ -53,6 +54,18 @@ class Grads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dopacity", "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh",
         "d_dL_dscales", "d_dL_drotations")]
+
+
+class FrostingParams(C.Structure):
+    _fields_ = [("P", C.c_int32), ("n_verts", C.c_int32), ("n_faces", C.c_int32), ("sh_rest", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("d_bary_logits", "d_cells", "d_faces", "d_inner_verts", "d_outer_verts",
+                                          "d_opacity_logits", "d_log_scales", "d_quats", "d_sh_dc", "d_sh_rest",
+                                          "d_mask")]
+
+
+class FrostingGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_bary_logits", "d_inner_verts", "d_outer_verts", "d_opacity_logits",
+                                          "d_log_scales", "d_quats", "d_sh_dc", "d_sh_rest")]
 
 
 class Layout(C.Structure):
@@ -104,6 +117,11 @@ def lib():
     L.fb200_gaussian_mask_from_faces.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                                  C.c_void_p, C.c_void_p]
     L.fb200_get_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Layout)]
+    L.fb200_frosting_attributes.argtypes = [C.POINTER(FrostingParams)] + [C.c_void_p] * 6
+    L.fb200_frosting_attributes.restype = C.c_int
+    L.fb200_frosting_attributes_backward.argtypes = [C.POINTER(FrostingParams)] + [C.c_void_p] * 5 + \
+        [C.POINTER(FrostingGrads), C.c_void_p]
+    L.fb200_frosting_attributes_backward.restype = C.c_int
     L.fb200_profile_enable.argtypes = [C.c_int32]
     L.fb200_profile_enable.restype = C.c_int
     L.fb200_profile_read.argtypes = [C.POINTER(C.c_float)]

@@ -311,4 +311,41 @@ int fb200_gaussian_mask_from_faces(int32_t n_points, const int64_t* d_point_cell
                  "gaussian_mask_from_faces");
 }
 
+static int check_frosting(const fb200_frosting_params* fp) {
+    if (!fp) return fail(FB200_EINVAL, "frosting_attributes: null params%s");
+    if (fp->P < 0 || fp->sh_rest < 0 || fp->n_verts < 0 || fp->n_faces < 0)
+        return fail(FB200_EINVAL, "frosting_attributes: bad extents%s");
+    if (fp->P > 0 && (!fp->d_bary_logits || !fp->d_cells || !fp->d_faces || !fp->d_inner_verts || !fp->d_outer_verts ||
+                      !fp->d_opacity_logits || !fp->d_log_scales || !fp->d_quats || !fp->d_sh_dc ||
+                      (fp->sh_rest > 0 && !fp->d_sh_rest)))
+        return fail(FB200_EINVAL, "frosting_attributes: missing parameter pointer%s");
+    return FB200_OK;
+}
+
+int fb200_frosting_attributes(const fb200_frosting_params* fp, float* d_means3D, float* d_opacities, float* d_scales,
+                              float* d_rotations, float* d_shs, void* stream) {
+    int rc = check_frosting(fp);
+    if (rc != FB200_OK) return rc;
+    if (fp->P > 0 && (!d_means3D || !d_opacities || !d_scales || !d_rotations || !d_shs))
+        return fail(FB200_EINVAL, "frosting_attributes: missing output pointer%s");
+    return check(launch_frosting_attr_fwd(*fp, d_means3D, d_opacities, d_scales, d_rotations, d_shs,
+                                          static_cast<cudaStream_t>(stream)), "frosting_attributes");
+}
+
+int fb200_frosting_attributes_backward(const fb200_frosting_params* fp, const float* d_g_means3D,
+                                       const float* d_g_opacities, const float* d_g_scales,
+                                       const float* d_g_rotations, const float* d_g_shs,
+                                       const fb200_frosting_grads* grads, void* stream) {
+    int rc = check_frosting(fp);
+    if (rc != FB200_OK) return rc;
+    if (!grads) return fail(FB200_EINVAL, "frosting_attributes_backward: null grads%s");
+    if (fp->P > 0 && (!d_g_means3D || !d_g_opacities || !d_g_scales || !d_g_rotations || !d_g_shs ||
+                      !grads->d_bary_logits || !grads->d_opacity_logits || !grads->d_log_scales || !grads->d_quats ||
+                      !grads->d_sh_dc || (fp->sh_rest > 0 && !grads->d_sh_rest) ||
+                      ((grads->d_inner_verts == nullptr) != (grads->d_outer_verts == nullptr))))
+        return fail(FB200_EINVAL, "frosting_attributes_backward: missing pointer%s");
+    return check(launch_frosting_attr_bwd(*fp, d_g_means3D, d_g_opacities, d_g_scales, d_g_rotations, d_g_shs, *grads,
+                                          static_cast<cudaStream_t>(stream)), "frosting_attributes_backward");
+}
+
 }  // extern "C"

@@ -1,0 +1,183 @@
+// frosting_attr.cu -- Frosting's per-frame attribute construction, fused.
+//
+// Replaces the chain of torch ops behind Frosting's properties
+//   bary_coords  frosting_scene/frosting_model.py:713-719  softmax over the 6 prism-cell logits
+//   points       :721-726   sum_k bary_k * shell_cells_verts[cell][k]   (inner v0..v2, outer v0..v2, :705-710)
+//   strengths    :729-730   sigmoid
+//   sh_coordinates :733-734 cat(dc[P,1,3], rest[P,M-1,3])
+//   scaling      :765       exp
+//   quaternions  :798       normalize
+// (softmax, index, mul, sum, sigmoid, exp, normalize, cat and their ~10 backward kernels; the cat alone
+// copies 192 B per Gaussian each way) by one forward and one backward kernel.  An optional occlusion mask
+// skips the Gaussians the rasterizer will drop anyway.  Values are tolerance-level (torch's own softmax /
+// normalize roundings are not part of the reference rasterizer's bit-exact contract): 1e-6 relative.
+#include "common.cuh"
+
+namespace fb200 {
+
+namespace {
+
+struct AttrArgs {
+    fb200_frosting_params p;
+    float* means3D; float* opacities; float* scales; float* rotations; float* shs;
+};
+
+struct AttrBwdArgs {
+    fb200_frosting_params p;
+    const float* g_means3D; const float* g_opacities; const float* g_scales; const float* g_rotations; const float* g_shs;
+    float* g_bary; float* g_inner; float* g_outer; float* g_opacity_logits; float* g_log_scales; float* g_quats;
+    float* g_sh_dc; float* g_sh_rest;
+};
+
+__device__ __forceinline__ void softmax6(const float* __restrict__ l, float* w) {
+    float m = l[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) m = fmaxf(m, l[k]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { w[k] = expf(l[k] - m); s += w[k]; }
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k] *= inv;
+}
+
+__global__ void __launch_bounds__(256)
+frosting_attr_fwd_kernel(AttrArgs a) {
+    const int P = a.p.P;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    if (a.p.d_mask != nullptr && a.p.d_mask[idx] == 0) return;
+    const size_t i = (size_t)idx;
+    // position
+    float l[6], w[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
+    softmax6(l, w);
+    const long long cell = a.p.d_cells[i];
+    const int v0 = a.p.d_faces[3 * cell], v1 = a.p.d_faces[3 * cell + 1], v2 = a.p.d_faces[3 * cell + 2];
+    const int vid[3] = {v0, v1, v2};
+    float px = 0.f, py = 0.f, pz = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* vi = a.p.d_inner_verts + 3 * (size_t)vid[k];
+        const float* vo = a.p.d_outer_verts + 3 * (size_t)vid[k];
+        px += w[k] * __ldg(vi) + w[3 + k] * __ldg(vo);
+        py += w[k] * __ldg(vi + 1) + w[3 + k] * __ldg(vo + 1);
+        pz += w[k] * __ldg(vi + 2) + w[3 + k] * __ldg(vo + 2);
+    }
+    a.means3D[3 * i] = px; a.means3D[3 * i + 1] = py; a.means3D[3 * i + 2] = pz;
+    // opacity, scale, rotation
+    a.opacities[i] = 1.0f / (1.0f + expf(-__ldg(a.p.d_opacity_logits + i)));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.scales[3 * i + k] = expf(__ldg(a.p.d_log_scales + 3 * i + k));
+    const float4 q = __ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i);
+    const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);   // F.normalize eps
+    reinterpret_cast<float4*>(a.rotations)[i] = make_float4(q.x / nrm, q.y / nrm, q.z / nrm, q.w / nrm);
+    // SH: dc | rest -> [M,3]
+    const int R = a.p.sh_rest;
+    float* sh = a.shs + i * (size_t)(R + 1) * 3;
+    sh[0] = __ldg(a.p.d_sh_dc + 3 * i); sh[1] = __ldg(a.p.d_sh_dc + 3 * i + 1); sh[2] = __ldg(a.p.d_sh_dc + 3 * i + 2);
+    const float* rest = a.p.d_sh_rest + i * (size_t)R * 3;
+    for (int k = 0; k < 3 * R; ++k) sh[3 + k] = __ldg(rest + k);
+}
+
+__global__ void __launch_bounds__(256)
+frosting_attr_bwd_kernel(AttrBwdArgs a) {
+    const int P = a.p.P;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const size_t i = (size_t)idx;
+    const int R = a.p.sh_rest;
+    const bool masked = a.p.d_mask != nullptr && a.p.d_mask[idx] == 0;
+    if (masked) {   // a dropped Gaussian receives zero gradient everywhere
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.g_bary[6 * i + k] = 0.f;
+        a.g_opacity_logits[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a.g_log_scales[3 * i + k] = 0.f; a.g_sh_dc[3 * i + k] = 0.f; }
+        reinterpret_cast<float4*>(a.g_quats)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3 * R; ++k) a.g_sh_rest[i * (size_t)R * 3 + k] = 0.f;
+        return;
+    }
+    // position: d/dw_k = <g, vert_k>, softmax backward, vertices get w_k * g (scatter-add)
+    float l[6], w[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
+    softmax6(l, w);
+    const float gx = a.g_means3D[3 * i], gy = a.g_means3D[3 * i + 1], gz = a.g_means3D[3 * i + 2];
+    const long long cell = a.p.d_cells[i];
+    const int vid[3] = {a.p.d_faces[3 * cell], a.p.d_faces[3 * cell + 1], a.p.d_faces[3 * cell + 2]};
+    float dw[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* vi = a.p.d_inner_verts + 3 * (size_t)vid[k];
+        const float* vo = a.p.d_outer_verts + 3 * (size_t)vid[k];
+        dw[k] = gx * __ldg(vi) + gy * __ldg(vi + 1) + gz * __ldg(vi + 2);
+        dw[3 + k] = gx * __ldg(vo) + gy * __ldg(vo + 1) + gz * __ldg(vo + 2);
+        if (a.g_inner != nullptr && (gx != 0.f || gy != 0.f || gz != 0.f)) {
+            float* di = a.g_inner + 3 * (size_t)vid[k];
+            float* dout = a.g_outer + 3 * (size_t)vid[k];
+            atomicAdd(di, w[k] * gx); atomicAdd(di + 1, w[k] * gy); atomicAdd(di + 2, w[k] * gz);
+            atomicAdd(dout, w[3 + k] * gx); atomicAdd(dout + 1, w[3 + k] * gy); atomicAdd(dout + 2, w[3 + k] * gz);
+        }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dot += w[k] * dw[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.g_bary[6 * i + k] = w[k] * (dw[k] - dot);
+    // sigmoid, exp
+    const float s = 1.0f / (1.0f + expf(-__ldg(a.p.d_opacity_logits + i)));
+    a.g_opacity_logits[i] = a.g_opacities[i] * s * (1.0f - s);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        a.g_log_scales[3 * i + k] = a.g_scales[3 * i + k] * expf(__ldg(a.p.d_log_scales + 3 * i + k));
+    // normalize: d/dq = (g - n <n, g>) / |q|
+    const float4 q = __ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i);
+    const float4 g = reinterpret_cast<const float4*>(a.g_rotations)[i];
+    const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    const float nx = q.x / nrm, ny = q.y / nrm, nz = q.z / nrm, nw = q.w / nrm;
+    const float ng = nx * g.x + ny * g.y + nz * g.z + nw * g.w;
+    reinterpret_cast<float4*>(a.g_quats)[i] =
+        make_float4((g.x - nx * ng) / nrm, (g.y - ny * ng) / nrm, (g.z - nz * ng) / nrm, (g.w - nw * ng) / nrm);
+    // SH split
+    const float* gsh = a.g_shs + i * (size_t)(R + 1) * 3;
+    a.g_sh_dc[3 * i] = gsh[0]; a.g_sh_dc[3 * i + 1] = gsh[1]; a.g_sh_dc[3 * i + 2] = gsh[2];
+    float* grest = a.g_sh_rest + i * (size_t)R * 3;
+    for (int k = 0; k < 3 * R; ++k) grest[k] = gsh[3 + k];
+}
+
+}  // namespace
+
+cudaError_t launch_frosting_attr_fwd(const fb200_frosting_params& p, float* means3D, float* opacities, float* scales,
+                                     float* rotations, float* shs, cudaStream_t s) {
+    if (p.P > 0) {
+        AttrArgs a; a.p = p; a.means3D = means3D; a.opacities = opacities; a.scales = scales; a.rotations = rotations; a.shs = shs;
+        frosting_attr_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(a);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frosting_attr_bwd(const fb200_frosting_params& p, const float* g_means3D, const float* g_opacities,
+                                     const float* g_scales, const float* g_rotations, const float* g_shs,
+                                     const fb200_frosting_grads& g, cudaStream_t s) {
+    if (g.d_inner_verts != nullptr && p.n_verts > 0) {
+        cudaError_t e = cudaMemsetAsync(g.d_inner_verts, 0, sizeof(float) * 3 * (size_t)p.n_verts, s);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(g.d_outer_verts, 0, sizeof(float) * 3 * (size_t)p.n_verts, s);
+        if (e != cudaSuccess) return e;
+    }
+    if (p.P > 0) {
+        AttrBwdArgs a; a.p = p;
+        a.g_means3D = g_means3D; a.g_opacities = g_opacities; a.g_scales = g_scales; a.g_rotations = g_rotations; a.g_shs = g_shs;
+        a.g_bary = g.d_bary_logits; a.g_inner = g.d_inner_verts; a.g_outer = g.d_outer_verts;
+        a.g_opacity_logits = g.d_opacity_logits; a.g_log_scales = g.d_log_scales; a.g_quats = g.d_quats;
+        a.g_sh_dc = g.d_sh_dc; a.g_sh_rest = g.d_sh_rest;
+        frosting_attr_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(a);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fb200

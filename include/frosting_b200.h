@@ -159,6 +159,39 @@ int fb200_gaussian_mask_from_faces(int32_t n_points, const int64_t* d_point_cell
                                    int32_t F, const uint8_t* d_face_visible, int32_t n_background,
                                    uint8_t* d_mask, void* stream);
 
+/* Frosting's per-frame attribute construction, fused (frosting_scene/frosting_model.py:713-799): turns the
+ * model's learnable parameters into the rasterizer inputs in one kernel (and one backward kernel) instead
+ * of the softmax / gather / mul / sum / sigmoid / exp / normalize / cat chain of torch ops. */
+typedef struct fb200_frosting_params {
+    int32_t P;                       /* mesh-bound Gaussians */
+    int32_t n_verts, n_faces;        /* shell base mesh */
+    int32_t sh_rest;                 /* M - 1: coefficients in _sh_coordinates_rest */
+    const float* d_bary_logits;      /* [P,6]  _bary_coords (softmax logits, :713-716) */
+    const int64_t* d_cells;          /* [P]    _point_cell_indices */
+    const int32_t* d_faces;          /* [F,3]  _shell_base_faces */
+    const float* d_inner_verts;      /* [V,3]  inner_verts property (:679-710) */
+    const float* d_outer_verts;      /* [V,3]  outer_verts */
+    const float* d_opacity_logits;   /* [P]    _opacities */
+    const float* d_log_scales;       /* [P,3]  _scales (scale_activation = exp, :32) */
+    const float* d_quats;            /* [P,4]  _quaternions (raw) */
+    const float* d_sh_dc;            /* [P,1,3] */
+    const float* d_sh_rest;          /* [P,M-1,3] */
+    const uint8_t* d_mask;           /* optional [P]: 0 = occluded, outputs for it are left untouched */
+} fb200_frosting_params;
+
+typedef struct fb200_frosting_grads {      /* all fully written; inner/outer vertex gradients are accumulated */
+    float* d_bary_logits; float* d_inner_verts; float* d_outer_verts; float* d_opacity_logits;
+    float* d_log_scales; float* d_quats; float* d_sh_dc; float* d_sh_rest;
+} fb200_frosting_grads;
+
+int fb200_frosting_attributes(const fb200_frosting_params* fp, float* d_means3D /*[P,3]*/, float* d_opacities /*[P,1]*/,
+                              float* d_scales /*[P,3]*/, float* d_rotations /*[P,4]*/, float* d_shs /*[P,M,3]*/,
+                              void* stream);
+int fb200_frosting_attributes_backward(const fb200_frosting_params* fp, const float* d_g_means3D,
+                                       const float* d_g_opacities, const float* d_g_scales,
+                                       const float* d_g_rotations, const float* d_g_shs,
+                                       const fb200_frosting_grads* grads, void* stream);
+
 /* Introspection for parity tests: byte offsets of the internal arrays inside the caller's buffers,
  * so tests can compare depth bits / rects / records / ranges / point_list with the reference's
  * geomBuffer / binningBuffer / imgBuffer one-to-one. */

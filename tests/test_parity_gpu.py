@@ -267,3 +267,62 @@ def test_equal_depth_ties_follow_gaussian_index(cuda_device):
     assert torch.equal(st["point_list"], refdgr.binning_views(ref["binning"], R)["point_list"])
     assert torch.equal(st["n_contrib"], refdgr.img_views(ref["img"], H, W)["n_contrib"])
     assert (st["color"] - ref["color"]).abs().max().item() <= 1e-4
+
+
+def test_fused_frosting_attributes_match_torch_chain(cuda_device):
+    """Row a20: one kernel vs Frosting's softmax/gather/sum/sigmoid/exp/normalize/cat chain
+    (frosting_scene/frosting_model.py:713-799, restated in scenes.frosting_attributes): values 1e-6, gradients 1e-5
+    relative to scale, incl. the scatter-added shell-vertex gradients; masked rows get zero gradient."""
+    dev = cuda_device
+    from frosting_b200 import scenes
+    cam = scenes.make_camera(200, 120, device=dev)
+    params, mesh = scenes.frosting_layer(30_000, cam, 11, n_faces_target=5000, device=dev)
+    gen = torch.Generator().manual_seed(5)
+    cots = {k: torch.randn(s, generator=gen).to(dev) for k, s in
+            dict(means3D=(30_000, 3), opacities=(30_000, 1), scales=(30_000, 3), rotations=(30_000, 4), shs=(30_000, 16, 3)).items()}
+
+    def run(fn, mask):
+        p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        m = dict(mesh); m["inner"] = mesh["inner"].clone().requires_grad_(True); m["outer"] = mesh["outer"].clone().requires_grad_(True)
+        out = fn(p, m) if mask is None else fn(p, m, mask)
+        w = 1.0 if mask is None else mask.float()
+        loss = sum(((out[k] * cots[k]).reshape(30_000, -1).sum(1) * w).sum() for k in cots)
+        loss.backward()
+        grads = {k: v.grad for k, v in p.items()}
+        grads["inner"], grads["outer"] = m["inner"].grad, m["outer"].grad
+        return {k: v.detach() for k, v in out.items()}, grads
+
+    ref_out, ref_g = run(scenes.frosting_attributes, None)
+    out, g = run(fb.frosting_attributes_fused, None)
+    for k in ref_out:
+        assert out[k].shape == ref_out[k].shape
+        assert (out[k] - ref_out[k]).abs().max().item() <= 1e-6 * max(1.0, ref_out[k].abs().max().item()), k
+    for k in ref_g:
+        scale = ref_g[k].abs().max().item()
+        assert (g[k] - ref_g[k]).abs().max().item() <= 2e-5 * scale, (k, (g[k] - ref_g[k]).abs().max().item() / scale)
+    # masked variant: kept rows identical, dropped rows contribute nothing
+    mask = torch.rand(30_000, generator=gen).to(dev) < 0.4
+    out_m, g_m = run(fb.frosting_attributes_fused, mask)
+
+    def ref_masked(p, m):
+        return scenes.frosting_attributes(p, m)
+    ro, rg = run(lambda p, m, mk: scenes.frosting_attributes(p, m), mask)
+    for k in ro:
+        assert (out_m[k][mask] - ro[k][mask]).abs().max().item() <= 1e-6 * max(1.0, ro[k].abs().max().item()), k
+    for k in rg:
+        scale = rg[k].abs().max().item()
+        assert (g_m[k] - rg[k]).abs().max().item() <= 2e-5 * scale, (k, "masked")
+    # end to end: fused attributes + in-kernel mask feed the rasterizer exactly like the torch chain + gathers
+    rs = scenes.settings_for(cam, 3, device=dev)
+    a1 = fb.frosting_attributes_fused(params, mesh, mask)
+    a2 = scenes.frosting_attributes(params, mesh)
+    r = fb.GaussianRasterizer(rs)
+    z = torch.zeros(30_000, 3, device=dev)
+    c1, _ = r(means3D=a1["means3D"], means2D=z, opacities=a1["opacities"], shs=a1["shs"], scales=a1["scales"],
+              rotations=a1["rotations"], visibility_mask=mask)
+    c2, _ = r(means3D=a2["means3D"][mask], means2D=z[mask], opacities=a2["opacities"][mask], shs=a2["shs"][mask],
+              scales=a2["scales"][mask], rotations=a2["rotations"][mask])
+    # the two attribute paths agree to ~1 ulp, which is enough to flip an alpha < 1/255 or tile-rect decision
+    # for a handful of pixel/Gaussian pairs (each worth up to ~4e-3): compare statistically
+    d = (c1 - c2).abs()
+    assert (d > 1e-4).float().mean().item() < 1e-3 and d.max().item() < 2e-2
