@@ -116,6 +116,7 @@ def build_workload(name, device, rank, world):
         params, mesh = scenes.frosting_layer(P, cam0, seed, n_faces_target=max(1000, P // 2), device="cpu")
         attrs = scenes.frosting_attributes(params, mesh)
         wl["mesh"] = {k: v.to(device) for k, v in mesh.items()}
+        wl["params"] = {k: v.to(device) for k, v in params.items()}
     else:
         attrs = scenes.random_gaussians(P, cam0, seed, device="cpu")
         # spread the free Gaussians around the ring centre so every ring camera sees a similar load
@@ -192,6 +193,50 @@ class ReferenceStep:
             # frosting_model.py:1564-1586: _index_mask[_point_cell_indices], then boolean gathers
             render_mask = self.wl["face_visible"][i].bool()[self.cells]
             m3, op, sh, sc, ro = m3[render_mask], op[render_mask], sh[render_mask], sc[render_mask], ro[render_mask]
+        means2D = torch.zeros_like(m3, requires_grad=True)
+        color, radii = self.refdgr.RefRasterize.apply(m3, means2D, sh, op, sc, ro, rs)
+        loss = (color * cot).sum()
+        loss.backward()
+        return loss.detach()
+
+
+class OursFrostingStep(OursStep):
+    """Frame as Frosting's refinement loop sees it (refine.py:487-518): learnable parameters -> attributes (row a20,
+    fused kernel) -> occlusion mask -> rasterizer -> loss -> backward down to the parameters."""
+
+    def __init__(self, wl, device):
+        super().__init__(wl, device)
+        self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
+
+    def __call__(self, i, rs, cot):
+        fb = self.fb
+        for v in self.params.values():
+            v.grad = None
+        mask = fb.gaussian_render_mask(self.wl["face_visible"][i], self.wl["mesh"]["cells"], self.P)
+        a = fb.frosting_attributes_fused(self.params, self.wl["mesh"], mask)
+        means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
+        color, radii = fb.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=means2D, opacities=a["opacities"],
+                                                 shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
+                                                 visibility_mask=mask)
+        loss = (color * cot).sum()
+        loss.backward()
+        return loss.detach()
+
+
+class ReferenceFrostingStep(ReferenceStep):
+    """Same frame through the reference's own chain: torch property ops (frosting_model.py:713-799), boolean
+    gathers (:1564-1586), reference rasterizer."""
+
+    def __init__(self, wl, device):
+        super().__init__(wl, device)
+        self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
+
+    def __call__(self, i, rs, cot):
+        for v in self.params.values():
+            v.grad = None
+        a = self.scenes.frosting_attributes(self.params, self.wl["mesh"])
+        render_mask = self.wl["face_visible"][i].bool()[self.cells]
+        m3, op, sh, sc, ro = (a[k][render_mask] for k in ("means3D", "opacities", "shs", "scales", "rotations"))
         means2D = torch.zeros_like(m3, requires_grad=True)
         color, radii = self.refdgr.RefRasterize.apply(m3, means2D, sh, op, sc, ro, rs)
         loss = (color * cot).sum()
@@ -357,6 +402,12 @@ def main():
 
     secs_e2e, _, _ = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=True)
     e2e_value = world * args.steps / secs_e2e
+    frosting_fps = None
+    if wl.get("params") is not None:
+        fstep = OursFrostingStep(wl, device) if args.impl == "ours" else ReferenceFrostingStep(wl, device)
+        secs_f, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
+        frosting_fps = world * args.steps / secs_f
+        del fstep
     H, W, P = wl["H"], wl["W"], wl["P"]
     h2d = 3 * H * W * 4 + (16 + 16 + 3 + 3) * 4
     d2h = 4
@@ -379,6 +430,10 @@ def main():
                         "stream, loss read back with .item(); model parameters stay resident as in the reference"},
         "gpu_launches": launches_timed,
     }
+    if frosting_fps is not None:
+        out["frosting_step"] = {"value": frosting_fps, "unit": UNIT,
+                                "note": "secondary: the same frame starting from Frosting's learnable parameters "
+                                        "(attribute construction, row a20, inside the step)"}
     if clocks:
         out["clocks"] = clocks
     if args.impl == "reference":

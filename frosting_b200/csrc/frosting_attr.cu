@@ -41,12 +41,36 @@ __device__ __forceinline__ void softmax6(const float* __restrict__ l, float* w) 
     for (int k = 0; k < 6; ++k) w[k] *= inv;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kAttrThreads = 128;
+constexpr int kMaxRest = 15;                       // SH degree 3: 15 "rest" coefficients -> 45 floats per row
+
+// The `rest` rows are 3*R floats (180 B for R = 15): only 4-byte aligned per row, but a warp's 32 rows are one
+// contiguous, 16-byte aligned block.  Full warps therefore move the block with coalesced 128-bit accesses
+// through shared memory (row stride 3R words is odd -> conflict-free scalar LDS/STS per lane); per-lane scalar
+// accesses at a 180-byte stride cost 32 LSU wavefronts per instruction and dominated the first version.
+__global__ void __launch_bounds__(kAttrThreads)
 frosting_attr_fwd_kernel(AttrArgs a) {
-    const int P = a.p.P;
+    __shared__ __align__(16) float stage[kAttrThreads / 32][32 * 3 * kMaxRest];
+    const unsigned full = 0xffffffffu;
+    const int P = a.p.P, R = a.p.sh_rest;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    if (a.p.d_mask != nullptr && a.p.d_mask[idx] == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g0 = idx - lane;
+    const bool in_range = idx < P;
+    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0);
+    const unsigned live_mask = __ballot_sync(full, live);
+    if (live_mask == 0) return;
+    // stage the warp's rest block when the warp is full and at least half of its rows are needed
+    const bool staged = (g0 + 31 < P) && R > 0 && R <= kMaxRest && ((3 * R * 32) % 4 == 0) && __popc(live_mask) >= 16;
+    float* srow = stage[warp];
+    if (staged) {
+        const float4* src = reinterpret_cast<const float4*>(a.p.d_sh_rest + (size_t)g0 * R * 3);
+        float4* dst = reinterpret_cast<float4*>(srow);
+        const int n4 = 3 * R * 32 / 4;
+        for (int f = lane; f < n4; f += 32) dst[f] = __ldg(src + f);
+        __syncwarp();
+    }
+    if (!live) return;
     const size_t i = (size_t)idx;
     // position
     float l[6], w[6];
@@ -54,8 +78,7 @@ frosting_attr_fwd_kernel(AttrArgs a) {
     for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
     softmax6(l, w);
     const long long cell = a.p.d_cells[i];
-    const int v0 = a.p.d_faces[3 * cell], v1 = a.p.d_faces[3 * cell + 1], v2 = a.p.d_faces[3 * cell + 2];
-    const int vid[3] = {v0, v1, v2};
+    const int vid[3] = {a.p.d_faces[3 * cell], a.p.d_faces[3 * cell + 1], a.p.d_faces[3 * cell + 2]};
     float px = 0.f, py = 0.f, pz = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -74,77 +97,134 @@ frosting_attr_fwd_kernel(AttrArgs a) {
     const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);   // F.normalize eps
     reinterpret_cast<float4*>(a.rotations)[i] = make_float4(q.x / nrm, q.y / nrm, q.z / nrm, q.w / nrm);
     // SH: dc | rest -> [M,3]
-    const int R = a.p.sh_rest;
     float* sh = a.shs + i * (size_t)(R + 1) * 3;
-    sh[0] = __ldg(a.p.d_sh_dc + 3 * i); sh[1] = __ldg(a.p.d_sh_dc + 3 * i + 1); sh[2] = __ldg(a.p.d_sh_dc + 3 * i + 2);
-    const float* rest = a.p.d_sh_rest + i * (size_t)R * 3;
-    for (int k = 0; k < 3 * R; ++k) sh[3 + k] = __ldg(rest + k);
+    const float d0 = __ldg(a.p.d_sh_dc + 3 * i), d1 = __ldg(a.p.d_sh_dc + 3 * i + 1), d2 = __ldg(a.p.d_sh_dc + 3 * i + 2);
+    if (R == kMaxRest) {
+        // 48 output floats = twelve aligned 128-bit stores
+        const float* rest = staged ? srow + lane * 45 : a.p.d_sh_rest + i * 45;
+        float o[48];
+        o[0] = d0; o[1] = d1; o[2] = d2;
+#pragma unroll
+        for (int k = 0; k < 45; ++k) o[3 + k] = staged ? rest[k] : __ldg(rest + k);
+        float4* sh4 = reinterpret_cast<float4*>(sh);
+#pragma unroll
+        for (int q4 = 0; q4 < 12; ++q4) sh4[q4] = make_float4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+    } else {
+        sh[0] = d0; sh[1] = d1; sh[2] = d2;
+        const float* rest = a.p.d_sh_rest + i * (size_t)R * 3;
+        for (int k = 0; k < 3 * R; ++k) sh[3 + k] = staged ? srow[lane * 3 * R + k] : __ldg(rest + k);
+    }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kAttrThreads)
 frosting_attr_bwd_kernel(AttrBwdArgs a) {
-    const int P = a.p.P;
+    __shared__ __align__(16) float stage[kAttrThreads / 32][32 * 3 * kMaxRest];
+    const unsigned full = 0xffffffffu;
+    const int P = a.p.P, R = a.p.sh_rest;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const size_t i = (size_t)idx;
-    const int R = a.p.sh_rest;
-    const bool masked = a.p.d_mask != nullptr && a.p.d_mask[idx] == 0;
-    if (masked) {   // a dropped Gaussian receives zero gradient everywhere
-#pragma unroll
-        for (int k = 0; k < 6; ++k) a.g_bary[6 * i + k] = 0.f;
-        a.g_opacity_logits[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { a.g_log_scales[3 * i + k] = 0.f; a.g_sh_dc[3 * i + k] = 0.f; }
-        reinterpret_cast<float4*>(a.g_quats)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < 3 * R; ++k) a.g_sh_rest[i * (size_t)R * 3 + k] = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g0 = idx - lane;
+    const bool full_warp = g0 + 31 < P;
+    const bool in_range = idx < P;
+    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0);
+    const unsigned live_mask = __ballot_sync(full, live);
+    const size_t i = (size_t)(in_range ? idx : 0);
+    float* srow = stage[warp];
+    const bool vec_rest = full_warp && R > 0 && R <= kMaxRest && ((3 * R * 32) % 4 == 0);
+
+    if (full_warp && live_mask == 0) {
+        // every Gaussian of the warp is occluded: coalesced zero fill of all parameter gradients
+        const size_t g = (size_t)g0;
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* p;
+        p = reinterpret_cast<float4*>(a.g_bary + 6 * g);           for (int f = lane; f < 48; f += 32) p[f] = z4;
+        p = reinterpret_cast<float4*>(a.g_opacity_logits + g);     if (lane < 8) p[lane] = z4;
+        p = reinterpret_cast<float4*>(a.g_log_scales + 3 * g);     if (lane < 24) p[lane] = z4;
+        p = reinterpret_cast<float4*>(a.g_quats + 4 * g);          p[lane] = z4;
+        p = reinterpret_cast<float4*>(a.g_sh_dc + 3 * g);          if (lane < 24) p[lane] = z4;
+        if (vec_rest) {
+            p = reinterpret_cast<float4*>(a.g_sh_rest + (size_t)R * 3 * g);
+            for (int f = lane; f < 3 * R * 8; f += 32) p[f] = z4;
+        } else {
+            for (int k = lane; k < 3 * R * 32; k += 32) a.g_sh_rest[(size_t)R * 3 * g + k] = 0.f;
+        }
         return;
     }
-    // position: d/dw_k = <g, vert_k>, softmax backward, vertices get w_k * g (scatter-add)
-    float l[6], w[6];
+
+    float gb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float g_op = 0.f, g_ls[3] = {0.f, 0.f, 0.f}, g_dc[3] = {0.f, 0.f, 0.f};
+    float4 g_q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        // position: d/dw_k = <g, vert_k>, softmax backward, vertices get w_k * g (scatter-add)
+        float l[6], w[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
-    softmax6(l, w);
-    const float gx = a.g_means3D[3 * i], gy = a.g_means3D[3 * i + 1], gz = a.g_means3D[3 * i + 2];
-    const long long cell = a.p.d_cells[i];
-    const int vid[3] = {a.p.d_faces[3 * cell], a.p.d_faces[3 * cell + 1], a.p.d_faces[3 * cell + 2]};
-    float dw[6];
+        for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
+        softmax6(l, w);
+        const float gx = a.g_means3D[3 * i], gy = a.g_means3D[3 * i + 1], gz = a.g_means3D[3 * i + 2];
+        const long long cell = a.p.d_cells[i];
+        const int vid[3] = {a.p.d_faces[3 * cell], a.p.d_faces[3 * cell + 1], a.p.d_faces[3 * cell + 2]};
+        float dw[6];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float* vi = a.p.d_inner_verts + 3 * (size_t)vid[k];
-        const float* vo = a.p.d_outer_verts + 3 * (size_t)vid[k];
-        dw[k] = gx * __ldg(vi) + gy * __ldg(vi + 1) + gz * __ldg(vi + 2);
-        dw[3 + k] = gx * __ldg(vo) + gy * __ldg(vo + 1) + gz * __ldg(vo + 2);
-        if (a.g_inner != nullptr && (gx != 0.f || gy != 0.f || gz != 0.f)) {
-            float* di = a.g_inner + 3 * (size_t)vid[k];
-            float* dout = a.g_outer + 3 * (size_t)vid[k];
-            atomicAdd(di, w[k] * gx); atomicAdd(di + 1, w[k] * gy); atomicAdd(di + 2, w[k] * gz);
-            atomicAdd(dout, w[3 + k] * gx); atomicAdd(dout + 1, w[3 + k] * gy); atomicAdd(dout + 2, w[3 + k] * gz);
+        for (int k = 0; k < 3; ++k) {
+            const float* vi = a.p.d_inner_verts + 3 * (size_t)vid[k];
+            const float* vo = a.p.d_outer_verts + 3 * (size_t)vid[k];
+            dw[k] = gx * __ldg(vi) + gy * __ldg(vi + 1) + gz * __ldg(vi + 2);
+            dw[3 + k] = gx * __ldg(vo) + gy * __ldg(vo + 1) + gz * __ldg(vo + 2);
+            if (a.g_inner != nullptr && (gx != 0.f || gy != 0.f || gz != 0.f)) {
+                float* di = a.g_inner + 3 * (size_t)vid[k];
+                float* dout = a.g_outer + 3 * (size_t)vid[k];
+                atomicAdd(di, w[k] * gx); atomicAdd(di + 1, w[k] * gy); atomicAdd(di + 2, w[k] * gz);
+                atomicAdd(dout, w[3 + k] * gx); atomicAdd(dout + 1, w[3 + k] * gy); atomicAdd(dout + 2, w[3 + k] * gz);
+            }
         }
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dot += w[k] * dw[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gb[k] = w[k] * (dw[k] - dot);
+        // sigmoid, exp
+        const float sg = 1.0f / (1.0f + expf(-__ldg(a.p.d_opacity_logits + i)));
+        g_op = a.g_opacities[i] * sg * (1.0f - sg);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g_ls[k] = a.g_scales[3 * i + k] * expf(__ldg(a.p.d_log_scales + 3 * i + k));
+        // normalize: d/dq = (g - n <n, g>) / |q|
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i);
+        const float4 g = reinterpret_cast<const float4*>(a.g_rotations)[i];
+        const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+        const float nx = q.x / nrm, ny = q.y / nrm, nz = q.z / nrm, nw = q.w / nrm;
+        const float ng = nx * g.x + ny * g.y + nz * g.z + nw * g.w;
+        g_q = make_float4((g.x - nx * ng) / nrm, (g.y - ny * ng) / nrm, (g.z - nz * ng) / nrm, (g.w - nw * ng) / nrm);
     }
-    float dot = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) dot += w[k] * dw[k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a.g_bary[6 * i + k] = w[k] * (dw[k] - dot);
-    // sigmoid, exp
-    const float s = 1.0f / (1.0f + expf(-__ldg(a.p.d_opacity_logits + i)));
-    a.g_opacity_logits[i] = a.g_opacities[i] * s * (1.0f - s);
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-        a.g_log_scales[3 * i + k] = a.g_scales[3 * i + k] * expf(__ldg(a.p.d_log_scales + 3 * i + k));
-    // normalize: d/dq = (g - n <n, g>) / |q|
-    const float4 q = __ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i);
-    const float4 g = reinterpret_cast<const float4*>(a.g_rotations)[i];
-    const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
-    const float nx = q.x / nrm, ny = q.y / nrm, nz = q.z / nrm, nw = q.w / nrm;
-    const float ng = nx * g.x + ny * g.y + nz * g.z + nw * g.w;
-    reinterpret_cast<float4*>(a.g_quats)[i] =
-        make_float4((g.x - nx * ng) / nrm, (g.y - ny * ng) / nrm, (g.z - nz * ng) / nrm, (g.w - nw * ng) / nrm);
-    // SH split
+    // SH split: dc gradient to registers, rest gradient rows to the staging block (or straight to memory)
     const float* gsh = a.g_shs + i * (size_t)(R + 1) * 3;
-    a.g_sh_dc[3 * i] = gsh[0]; a.g_sh_dc[3 * i + 1] = gsh[1]; a.g_sh_dc[3 * i + 2] = gsh[2];
-    float* grest = a.g_sh_rest + i * (size_t)R * 3;
-    for (int k = 0; k < 3 * R; ++k) grest[k] = gsh[3 + k];
+    if (live && R == kMaxRest) {
+        const float4* g4 = reinterpret_cast<const float4*>(gsh);
+        float o[48];
+#pragma unroll
+        for (int q4 = 0; q4 < 12; ++q4) { const float4 t = g4[q4]; o[4 * q4] = t.x; o[4 * q4 + 1] = t.y; o[4 * q4 + 2] = t.z; o[4 * q4 + 3] = t.w; }
+        g_dc[0] = o[0]; g_dc[1] = o[1]; g_dc[2] = o[2];
+        float* dst = vec_rest ? srow + lane * 45 : a.g_sh_rest + i * 45;
+#pragma unroll
+        for (int k = 0; k < 45; ++k) dst[k] = o[3 + k];
+    } else if (in_range) {
+        if (live) { g_dc[0] = gsh[0]; g_dc[1] = gsh[1]; g_dc[2] = gsh[2]; }
+        float* dst = vec_rest ? srow + lane * 3 * R : a.g_sh_rest + i * (size_t)R * 3;
+        for (int k = 0; k < 3 * R; ++k) dst[k] = live ? gsh[3 + k] : 0.f;
+    }
+    if (vec_rest) {
+        __syncwarp();
+        const float4* src = reinterpret_cast<const float4*>(srow);
+        float4* dst = reinterpret_cast<float4*>(a.g_sh_rest + (size_t)g0 * R * 3);
+        const int n4 = 3 * R * 32 / 4;
+        for (int f = lane; f < n4; f += 32) dst[f] = src[f];
+    }
+    if (!in_range) return;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.g_bary[6 * i + k] = gb[k];
+    a.g_opacity_logits[i] = g_op;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a.g_log_scales[3 * i + k] = g_ls[k]; a.g_sh_dc[3 * i + k] = g_dc[k]; }
+    reinterpret_cast<float4*>(a.g_quats)[i] = g_q;
 }
 
 }  // namespace
@@ -153,7 +233,7 @@ cudaError_t launch_frosting_attr_fwd(const fb200_frosting_params& p, float* mean
                                      float* rotations, float* shs, cudaStream_t s) {
     if (p.P > 0) {
         AttrArgs a; a.p = p; a.means3D = means3D; a.opacities = opacities; a.scales = scales; a.rotations = rotations; a.shs = shs;
-        frosting_attr_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(a);
+        frosting_attr_fwd_kernel<<<(p.P + kAttrThreads - 1) / kAttrThreads, kAttrThreads, 0, s>>>(a);
         count_launch();
     }
     return cudaGetLastError();
@@ -174,7 +254,7 @@ cudaError_t launch_frosting_attr_bwd(const fb200_frosting_params& p, const float
         a.g_bary = g.d_bary_logits; a.g_inner = g.d_inner_verts; a.g_outer = g.d_outer_verts;
         a.g_opacity_logits = g.d_opacity_logits; a.g_log_scales = g.d_log_scales; a.g_quats = g.d_quats;
         a.g_sh_dc = g.d_sh_dc; a.g_sh_rest = g.d_sh_rest;
-        frosting_attr_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(a);
+        frosting_attr_bwd_kernel<<<(p.P + kAttrThreads - 1) / kAttrThreads, kAttrThreads, 0, s>>>(a);
         count_launch();
     }
     return cudaGetLastError();
