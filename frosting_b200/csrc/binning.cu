@@ -70,7 +70,8 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
         cursor[t] = run;
         if (c > 1) {
             if (c <= (uint32_t)kSortSmallMax) list_small[atomicAdd(&s_n[0], 1u)] = t;
-            else list_large[atomicAdd(&s_n[1], 1u)] = t;
+            else if (c <= (uint32_t)kSortMediumMax) list_large[atomicAdd(&s_n[1], 1u)] = t;
+            else list_huge[atomicAdd(&s_n[2], 1u)] = t;
         }
         run += c;
     }
@@ -266,15 +267,19 @@ __device__ __forceinline__ void radix_sort_tile(u64* a, u64* b, int n,
     result = src;
 }
 
-template <int kThreads, int kMaxN>
+template <int kThreads, int kMaxN, bool kDynamic>
 __global__ void __launch_bounds__(kThreads)
 tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
                         const uint2* __restrict__ ranges, u64* __restrict__ keys,
                         uint32_t* __restrict__ point_list, const int32_t* __restrict__ status) {
-    __shared__ u64 buf_a[kMaxN];
-    __shared__ u64 buf_b[kMaxN];
-    __shared__ uint32_t counters[(kThreads / 32) * 256];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ u64 stat_a[kDynamic ? 1 : kMaxN];
+    __shared__ u64 stat_b[kDynamic ? 1 : kMaxN];
+    __shared__ uint32_t stat_counters[kDynamic ? 1 : (kThreads / 32) * 256];
     __shared__ uint32_t s_misc[16];
+    u64* buf_a = kDynamic ? reinterpret_cast<u64*>(dyn_smem) : stat_a;
+    u64* buf_b = kDynamic ? reinterpret_cast<u64*>(dyn_smem) + kMaxN : stat_b;
+    uint32_t* counters = kDynamic ? reinterpret_cast<uint32_t*>(dyn_smem + 2 * sizeof(u64) * kMaxN) : stat_counters;
     if (status[FB200_ST_OVERFLOW]) return;
     const uint32_t count = *n_list;
     for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
@@ -356,17 +361,28 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
         count_launch();
     }
     single_instance_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, a.ranges, a.keys, a.point_list, a.status);
-    count_launch(3);   // + the two sort kernels below
+    count_launch(4);   // + the three sort kernels below
     // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides
     // over its list.
     {
         const int grid = min(T, 148 * 5);
-        tile_sort_shared_kernel<256, kSortSmallMax><<<grid, 256, 0, s>>>(
+        tile_sort_shared_kernel<256, kSortSmallMax, false><<<grid, 256, 0, s>>>(
             a.list_small, a.counters + 0, a.ranges, a.keys, a.point_list, a.status);
     }
     {
+        // medium lists (2048 < n <= 8192): 1024 threads, ping-pong buffers + per-warp counters in 160 KB of
+        // dynamic shared memory, one CTA per SM
+        const int smem = 2 * 8 * kSortMediumMax + 32 * 256 * 4;
+        cudaError_t e = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortMediumMax, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        const int grid = min(T, 148);
+        tile_sort_shared_kernel<1024, kSortMediumMax, true><<<grid, 1024, smem, s>>>(
+            a.list_large, a.counters + 1, a.ranges, a.keys, a.point_list, a.status);
+    }
+    {
         const int grid = min(T, 148 * 2);
-        tile_sort_global_kernel<1024><<<grid, 1024, 0, s>>>(a.list_large, a.counters + 1, a.ranges, a.keys,
+        tile_sort_global_kernel<1024><<<grid, 1024, 0, s>>>(a.list_huge, a.counters + 2, a.ranges, a.keys,
                                                             a.keys_scratch, a.point_list, a.status);
     }
     return cudaGetLastError();
