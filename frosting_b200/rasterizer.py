@@ -43,6 +43,20 @@ NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove i
 
 
 _pinned = {}
+_size_cache = {}
+
+
+def _sizes(L, P, W, H):
+    """Workspace sizes rounded up to 512 bytes (so the carved sub-buffers keep torch's base alignment)."""
+    k = (P, W, H)
+    v = _size_cache.get(k)
+    if v is None:
+        r = lambda n: (int(n) + 511) // 512 * 512
+        v = (r(L.fb200_geom_bytes(P)), r(L.fb200_image_bytes(W, H)))
+        if len(_size_cache) > 64:
+            _size_cache.clear()
+        _size_cache[k] = v
+    return v
 
 
 def _pinned_status(device):
@@ -67,7 +81,7 @@ def _f32c(t: torch.Tensor, device, name: str) -> torch.Tensor:
         raise TypeError(f"{name} must be float32, got {t.dtype}")
     if t.device != device:
         t = t.to(device)
-    return t.contiguous()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 class _Call:
@@ -120,9 +134,10 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
         stream = torch.cuda.current_stream(device)
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         radii = torch.empty((P,), dtype=torch.int32, device=device)
-        geom = torch.empty((L.fb200_geom_bytes(P),), dtype=torch.uint8, device=device)
-        image = torch.empty((L.fb200_image_bytes(W, H),), dtype=torch.uint8, device=device)
-        status = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, device=device)
+        gb, ib = _sizes(L, P, W, H)
+        slab = torch.empty((gb + ib + 128,), dtype=torch.uint8, device=device)   # one allocator call
+        geom, image = slab[:gb], slab[gb:gb + ib]
+        status = slab[gb + ib:gb + ib + 4 * _lib.FB200_STATUS_WORDS].view(torch.int32)
         status_host = _pinned_status(device)
 
         # Phase 1: preprocess + tile scan.  The exact instance count R comes back through a pinned
@@ -165,15 +180,17 @@ def _launch_backward(call: "_Call", radii, grad_out_color):
         if g.dtype != torch.float32:
             g = g.float()
         g = g.contiguous()
-        opts = dict(dtype=torch.float32, device=device)
-        dL_dmeans3D = torch.empty((P, 3), **opts)
-        dL_dmeans2D = torch.empty((P, 3), **opts)
-        dL_dcolors = torch.empty((P, 3), **opts)
-        dL_dopacity = torch.empty((P, 1), **opts)
-        dL_dcov3D = torch.empty((P, 6), **opts)
-        dL_dsh = torch.empty((P, M, 3), **opts)
-        dL_dscales = torch.empty((P, 3), **opts)
-        dL_drotations = torch.empty((P, 4), **opts)
+        # one allocation carved into the eight gradient tensors (each offset is a multiple of 4 floats)
+        n = [3 * P, 3 * P, 3 * P, P, 6 * P, 3 * M * P, 3 * P, 4 * P]
+        offs, tot = [], 0
+        for c in n:
+            offs.append(tot)
+            tot += (c + 3) // 4 * 4
+        gslab = torch.empty((max(tot, 1),), dtype=torch.float32, device=device)
+        cut = lambda k, shape: gslab[offs[k]:offs[k] + n[k]].view(shape)
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors = cut(0, (P, 3)), cut(1, (P, 3)), cut(2, (P, 3))
+        dL_dopacity, dL_dcov3D, dL_dsh = cut(3, (P, 1)), cut(4, (P, 6)), cut(5, (P, M, 3))
+        dL_dscales, dL_drotations = cut(6, (P, 3)), cut(7, (P, 4))
         grads = Grads(d_dL_dmeans2D=_ptr(dL_dmeans2D), d_dL_dcolors=_ptr(dL_dcolors),
                       d_dL_dopacity=_ptr(dL_dopacity), d_dL_dmeans3D=_ptr(dL_dmeans3D),
                       d_dL_dcov3D=_ptr(dL_dcov3D), d_dL_dsh=_ptr(dL_dsh), d_dL_dscales=_ptr(dL_dscales),
