@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -80,7 +80,7 @@ class ClockSampler:
             return None
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [l.split(", ") for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15]
+        rows = [l.split(", ") for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.25]
         if not rows:
             rows = [l.split(", ") for (_, l) in self.lines[-3:]]
         sm, reasons, mx = [], set(), None
@@ -380,8 +380,8 @@ def cpu_baseline(wl, step, sample_cam=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
