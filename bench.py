@@ -211,6 +211,8 @@ class OursFrostingStep(OursStep):
     def __init__(self, wl, device):
         super().__init__(wl, device)
         self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
+        self.real_loss = False
+        self.gt = None
 
     def __call__(self, i, rs, cot):
         fb = self.fb
@@ -222,7 +224,10 @@ class OursFrostingStep(OursStep):
         color, radii = fb.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=means2D, opacities=a["opacities"],
                                                  shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
                                                  visibility_mask=mask)
-        loss = (color * cot).sum()
+        if self.real_loss:
+            loss = fb.l1_dssim_loss(color, self.gt[i], 0.2)          # fused L1 + D-SSIM (row f2)
+        else:
+            loss = (color * cot).sum()
         loss.backward()
         return loss.detach()
 
@@ -234,6 +239,8 @@ class ReferenceFrostingStep(ReferenceStep):
     def __init__(self, wl, device):
         super().__init__(wl, device)
         self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
+        self.real_loss = False
+        self.gt = None
 
     def __call__(self, i, rs, cot):
         for v in self.params.values():
@@ -243,7 +250,11 @@ class ReferenceFrostingStep(ReferenceStep):
         m3, op, sh, sc, ro = (a[k][render_mask] for k in ("means3D", "opacities", "shs", "scales", "rotations"))
         means2D = torch.zeros_like(m3, requires_grad=True)
         color, radii = self.refdgr.RefRasterize.apply(m3, means2D, sh, op, sc, ro, rs)
-        loss = (color * cot).sum()
+        if self.real_loss:
+            from frosting_b200.loss import torch_reference     # restates frosting_utils/loss_utils.py:17-63 verbatim
+            loss = torch_reference(color, self.gt[i], 0.2)
+        else:
+            loss = (color * cot).sum()
         loss.backward()
         return loss.detach()
 
@@ -429,6 +440,13 @@ def main():
         fstep = OursFrostingStep(wl, device) if args.impl == "ours" else ReferenceFrostingStep(wl, device)
         secs_f, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
         frosting_fps = world * args.steps / secs_f
+        # ... and with the trainers' real loss, 0.8 L1 + 0.2 (1 - SSIM) against a ground-truth image (refine.py:407-409)
+        gtg = torch.Generator().manual_seed(99 + rank)
+        fstep.gt = [torch.rand(3, wl["H"], wl["W"], generator=gtg).to(device) for _ in wl["cams"]]
+        fstep.real_loss = True
+        fstep.primed = False
+        secs_t, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
+        train_fps = world * args.steps / secs_t
         del fstep
     H, W, P = wl["H"], wl["W"], wl["P"]
     h2d = 3 * H * W * 4 + (16 + 16 + 3 + 3) * 4
@@ -457,6 +475,9 @@ def main():
         out["frosting_step"] = {"value": frosting_fps, "unit": UNIT,
                                 "note": "secondary: the same frame starting from Frosting's learnable parameters "
                                         "(attribute construction, row a20, inside the step)"}
+        out["frosting_train_step"] = {"value": train_fps, "unit": UNIT,
+                                      "note": "secondary: parameters -> attributes -> mask -> rasterizer -> 0.8 L1 + 0.2 (1-SSIM) "
+                                              "-> backward (ours: fused loss kernel, row f2; reference: its torch loss)"}
     if clocks:
         out["clocks"] = clocks
     if args.impl == "reference":

@@ -20,6 +20,7 @@ EXPORTED = [
     "fb200_mesh_visibility", "fb200_gaussian_mask_from_faces", "fb200_get_layout",
     "fb200_profile_enable", "fb200_profile_read", "fb200_kernel_launches",
     "fb200_frosting_attributes", "fb200_frosting_attributes_backward",
+    "fb200_loss_partials", "fb200_l1_dssim_forward", "fb200_l1_dssim_backward",
 ]
 NUM_STAGES = 5
 STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
@@ -122,6 +123,14 @@ def lib():
     L.fb200_frosting_attributes_backward.argtypes = [C.POINTER(FrostingParams)] + [C.c_void_p] * 5 + \
         [C.POINTER(FrostingGrads), C.c_void_p]
     L.fb200_frosting_attributes_backward.restype = C.c_int
+    L.fb200_loss_partials.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.fb200_loss_partials.restype = C.c_size_t
+    L.fb200_l1_dssim_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fb200_l1_dssim_forward.restype = C.c_int
+    L.fb200_l1_dssim_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fb200_l1_dssim_backward.restype = C.c_int
     L.fb200_profile_enable.argtypes = [C.c_int32]
     L.fb200_profile_enable.restype = C.c_int
     L.fb200_profile_read.argtypes = [C.POINTER(C.c_float)]

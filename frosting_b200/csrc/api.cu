@@ -348,4 +348,24 @@ int fb200_frosting_attributes_backward(const fb200_frosting_params* fp, const fl
                                           static_cast<cudaStream_t>(stream)), "frosting_attributes_backward");
 }
 
+size_t fb200_loss_partials(int32_t C, int32_t H, int32_t W) {
+    return (C > 0 && H > 0 && W > 0) ? l1_dssim_num_partials(C, H, W) : 0;
+}
+
+int fb200_l1_dssim_forward(const float* d_pred, const float* d_gt, int32_t C, int32_t H, int32_t W, float lambda,
+                           float* d_maps, float* d_partials, float* d_loss, void* stream) {
+    if (C <= 0 || H <= 0 || W <= 0 || !d_pred || !d_gt || !d_maps || !d_partials || !d_loss)
+        return fail(FB200_EINVAL, "l1_dssim_forward: bad arguments%s");
+    return check(launch_l1_dssim_fwd(d_pred, d_gt, C, H, W, lambda, d_maps, d_partials, d_loss,
+                                     static_cast<cudaStream_t>(stream)), "l1_dssim_forward");
+}
+
+int fb200_l1_dssim_backward(const float* d_pred, const float* d_gt, const float* d_maps, int32_t C, int32_t H,
+                            int32_t W, float lambda, const float* d_dL_dloss, float* d_dpred, void* stream) {
+    if (C <= 0 || H <= 0 || W <= 0 || !d_pred || !d_gt || !d_maps || !d_dL_dloss || !d_dpred)
+        return fail(FB200_EINVAL, "l1_dssim_backward: bad arguments%s");
+    return check(launch_l1_dssim_bwd(d_pred, d_gt, d_maps, C, H, W, lambda, d_dL_dloss, d_dpred,
+                                     static_cast<cudaStream_t>(stream)), "l1_dssim_backward");
+}
+
 }  // extern "C"

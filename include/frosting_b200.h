@@ -192,6 +192,16 @@ int fb200_frosting_attributes_backward(const fb200_frosting_params* fp, const fl
                                        const float* d_g_rotations, const float* d_g_shs,
                                        const fb200_frosting_grads* grads, void* stream);
 
+/* Fused photometric loss (1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y)) of Frosting's trainers
+ * (frosting_utils/loss_utils.py:17-63 with refine.py:407-409; 11x11 Gaussian window, sigma 1.5, zero padding).
+ *   d_pred, d_gt [C,H,W]; d_maps [3,C,H,W] scratch kept for backward; d_partials [fb200_loss_partials(C,H,W)];
+ *   d_loss [1].  Backward writes d(loss)/d(pred) scaled by the device scalar d_dL_dloss[0]. */
+size_t fb200_loss_partials(int32_t C, int32_t H, int32_t W);
+int fb200_l1_dssim_forward(const float* d_pred, const float* d_gt, int32_t C, int32_t H, int32_t W, float lambda,
+                           float* d_maps, float* d_partials, float* d_loss, void* stream);
+int fb200_l1_dssim_backward(const float* d_pred, const float* d_gt, const float* d_maps, int32_t C, int32_t H,
+                            int32_t W, float lambda, const float* d_dL_dloss, float* d_dpred, void* stream);
+
 /* Introspection for parity tests: byte offsets of the internal arrays inside the caller's buffers,
  * so tests can compare depth bits / rects / records / ranges / point_list with the reference's
  * geomBuffer / binningBuffer / imgBuffer one-to-one. */
