@@ -407,6 +407,7 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     if args.gpus != world and rank == 0:
         log(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: using WORLD_SIZE")
