@@ -398,6 +398,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: route fd 1 to stderr for the whole run (NCCL / C libraries print their
+    # banners there) and write the result to the saved descriptor at the end
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -416,7 +421,8 @@ def main():
         from oracle import refdgr
         if not refdgr.available():
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dgr_C.so not built (needs /root/reference)"}))
+                os.write(result_fd, (json.dumps({"impl": "reference", "unavailable":
+                                                 "oracle/_ref/ref_dgr_C.so not built (needs /root/reference)"}) + "\n").encode())
             return
 
     import frosting_b200 as fb
@@ -519,7 +525,7 @@ def main():
             except Exception as ex:
                 out["cpu_baseline_error"] = repr(ex)
     if rank == 0:
-        print(json.dumps(out))
+        os.write(result_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
