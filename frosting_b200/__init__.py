@@ -8,6 +8,7 @@ from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rast
                          forward_with_state)
 from .frosting_attrs import frosting_attributes_fused
 from .loss import l1_dssim_loss
+from .optim import FrostingAdam, OptimizationParams
 from .mesh import (MeshRasterizer, RasterizationSettings, Fragments, nvdiff_rasterization,
                    nvdiff_rasterization_with_pix_to_face, rasterize_mesh, gaussian_render_mask)
 
@@ -15,7 +16,7 @@ __all__ = [
     "GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "forward_with_state",
     "MeshRasterizer", "RasterizationSettings", "Fragments", "nvdiff_rasterization",
     "nvdiff_rasterization_with_pix_to_face", "rasterize_mesh", "gaussian_render_mask",
-    "install_as_diff_gaussian_rasterization", "frosting_attributes_fused", "l1_dssim_loss",
+    "install_as_diff_gaussian_rasterization", "frosting_attributes_fused", "l1_dssim_loss", "FrostingAdam", "OptimizationParams",
 ]
 
 

@@ -21,6 +21,7 @@ EXPORTED = [
     "fb200_profile_enable", "fb200_profile_read", "fb200_kernel_launches",
     "fb200_frosting_attributes", "fb200_frosting_attributes_backward",
     "fb200_loss_partials", "fb200_l1_dssim_forward", "fb200_l1_dssim_backward",
+    "fb200_adam_step", "fb200_peer_alloc", "fb200_peer_free", "fb200_peer_export", "fb200_peer_open", "fb200_peer_close",
 ]
 NUM_STAGES = 5
 STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
@@ -67,6 +68,21 @@ class FrostingParams(C.Structure):
 class FrostingGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_bary_logits", "d_inner_verts", "d_outer_verts", "d_opacity_logits",
                                           "d_log_scales", "d_quats", "d_sh_dc", "d_sh_rest")]
+
+
+ADAM_MAX_GROUPS = 16
+MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32),
+                ("peer_params", C.c_void_p * MAX_PEERS), ("peer_grads", C.c_void_p * MAX_PEERS),
+                ("d_exp_avg", C.c_void_p), ("d_exp_avg_sq", C.c_void_p),
+                ("shard_lo", C.c_int64), ("shard_hi", C.c_int64), ("n_groups", C.c_int32),
+                ("group_start", C.c_int64 * (ADAM_MAX_GROUPS + 1)), ("lr", C.c_float * ADAM_MAX_GROUPS),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("bias_correction1", C.c_float), ("bias_correction2_sqrt", C.c_float), ("grad_scale", C.c_float)]
 
 
 class Layout(C.Structure):
@@ -131,6 +147,15 @@ def lib():
     L.fb200_l1_dssim_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     L.fb200_l1_dssim_backward.restype = C.c_int
+    L.fb200_adam_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
+    L.fb200_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.fb200_peer_free.argtypes = [C.c_void_p]
+    L.fb200_peer_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.fb200_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.fb200_peer_close.argtypes = [C.c_void_p]
+    for n in ("fb200_adam_step", "fb200_peer_alloc", "fb200_peer_free", "fb200_peer_export", "fb200_peer_open",
+              "fb200_peer_close"):
+        getattr(L, n).restype = C.c_int
     L.fb200_profile_enable.argtypes = [C.c_int32]
     L.fb200_profile_enable.restype = C.c_int
     L.fb200_profile_read.argtypes = [C.POINTER(C.c_float)]

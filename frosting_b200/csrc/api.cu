@@ -368,4 +368,57 @@ int fb200_l1_dssim_backward(const float* d_pred, const float* d_gt, const float*
                                      static_cast<cudaStream_t>(stream)), "l1_dssim_backward");
 }
 
+int fb200_adam_step(const fb200_adam_args* a, void* stream) {
+    if (!a) return fail(FB200_EINVAL, "adam_step: null args%s");
+    if (a->world < 1 || a->world > FB200_MAX_PEERS || a->rank < 0 || a->rank >= a->world)
+        return fail(FB200_EINVAL, "adam_step: world must be 1..8 and rank inside it%s");
+    if (a->n_groups < 1 || a->n_groups > FB200_ADAM_MAX_GROUPS)
+        return fail(FB200_EINVAL, "adam_step: 1..16 parameter groups%s");
+    for (int g = 0; g <= a->n_groups; ++g)
+        if ((a->group_start[g] & 3) || (g > 0 && a->group_start[g] < a->group_start[g - 1]))
+            return fail(FB200_EINVAL, "adam_step: group starts must be ascending multiples of 4 elements%s");
+    if ((a->shard_lo & 3) || (a->shard_hi & 3) || a->shard_lo < a->group_start[0] || a->shard_hi < a->shard_lo ||
+        a->shard_hi > a->group_start[a->n_groups])
+        return fail(FB200_EINVAL, "adam_step: shard must be a 4-aligned range inside the slab%s");
+    if (a->shard_hi > a->shard_lo) {
+        if (!a->d_exp_avg || !a->d_exp_avg_sq) return fail(FB200_EINVAL, "adam_step: missing moment buffers%s");
+        for (int p = 0; p < a->world; ++p)
+            if (!a->peer_params[p] || !a->peer_grads[p]) return fail(FB200_EINVAL, "adam_step: missing slab pointer%s");
+    }
+    if (!(a->bias_correction1 > 0.f) || !(a->bias_correction2_sqrt > 0.f))
+        return fail(FB200_EINVAL, "adam_step: bias corrections must be positive (step >= 1)%s");
+    return check(launch_adam_shard(*a, static_cast<cudaStream_t>(stream)), "adam_step");
+}
+
+int fb200_peer_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes == 0) return fail(FB200_EINVAL, "peer_alloc: bad arguments%s");
+    void* p = nullptr;
+    int rc = check(cudaMalloc(&p, bytes), "peer_alloc");
+    if (rc != FB200_OK) return rc;
+    rc = check(cudaMemset(p, 0, bytes), "peer_alloc (zero-fill)");
+    if (rc != FB200_OK) { cudaFree(p); return rc; }
+    *d_ptr = p;
+    return FB200_OK;
+}
+
+int fb200_peer_free(void* d_ptr) { return d_ptr ? check(cudaFree(d_ptr), "peer_free") : FB200_OK; }
+
+int fb200_peer_export(void* d_ptr, unsigned char* handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == FB200_PEER_HANDLE_BYTES, "handle size");
+    if (!d_ptr || !handle) return fail(FB200_EINVAL, "peer_export: bad arguments%s");
+    cudaIpcMemHandle_t h;
+    int rc = check(cudaIpcGetMemHandle(&h, d_ptr), "peer_export");
+    if (rc == FB200_OK) memcpy(handle, &h, sizeof(h));
+    return rc;
+}
+
+int fb200_peer_open(const unsigned char* handle, void** d_ptr) {
+    if (!d_ptr || !handle) return fail(FB200_EINVAL, "peer_open: bad arguments%s");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    return check(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess), "peer_open");
+}
+
+int fb200_peer_close(void* d_ptr) { return d_ptr ? check(cudaIpcCloseMemHandle(d_ptr), "peer_close") : FB200_OK; }
+
 }  // extern "C"

@@ -22,7 +22,8 @@ def _p(t):
 
 class _FrostingAttributes(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, mask):
+    def forward(ctx, bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, mask,
+                sink=None):
         if not bary_logits.is_cuda:
             raise RuntimeError("frosting_b200 runs on CUDA tensors only (no CPU fallback)")
         dev = bary_logits.device
@@ -46,6 +47,7 @@ class _FrostingAttributes(torch.autograd.Function):
                 C.byref(fp), _p(means3D), _p(opac), _p(scales), _p(rots), _p(shs),
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         ctx.fp = fp
+        ctx.sink = sink
         ctx.keep = (bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, m)
         ctx.vert_grad = inner.requires_grad or outer.requires_grad
         return means3D, opac, scales, rots, shs
@@ -59,8 +61,18 @@ class _FrostingAttributes(torch.autograd.Function):
         z = lambda g, shape: torch.zeros(shape, **o) if g is None else g.contiguous()
         g_means3D, g_opac, g_scales = z(g_means3D, (P, 3)), z(g_opac, (P, 1)), z(g_scales, (P, 3))
         g_rots, g_shs = z(g_rots, (P, 4)), z(g_shs, (P, R + 1, 3))
-        d_bary, d_op, d_ls = torch.empty((P, 6), **o), torch.empty((P,), **o), torch.empty((P, 3), **o)
-        d_q, d_dc, d_rest = torch.empty((P, 4), **o), torch.empty((P, 1, 3), **o), torch.empty((P, R, 3), **o)
+        if ctx.sink is not None:
+            # gradients go straight into the optimizer's gradient slab (frosting_b200/optim.py); autograd gets None
+            k = ctx.sink
+            d_bary, d_op, d_ls = k["bary_logits"], k["opacity_logits"], k["log_scales"]
+            d_q, d_dc, d_rest = k["quats"], k["sh_dc"], k["sh_rest"]
+            for t, ref in ((d_bary, bary_logits), (d_op, opacity_logits), (d_ls, log_scales), (d_q, quats),
+                           (d_dc, sh_dc), (d_rest, sh_rest)):
+                if t.numel() != ref.numel() or not t.is_contiguous() or t.dtype != torch.float32 or t.device != dev:
+                    raise RuntimeError("grad_sink tensors must be contiguous fp32 CUDA tensors shaped like the parameters")
+        else:
+            d_bary, d_op, d_ls = torch.empty((P, 6), **o), torch.empty((P,), **o), torch.empty((P, 3), **o)
+            d_q, d_dc, d_rest = torch.empty((P, 4), **o), torch.empty((P, 1, 3), **o), torch.empty((P, R, 3), **o)
         d_in = torch.empty_like(inner) if ctx.vert_grad else None
         d_out = torch.empty_like(outer) if ctx.vert_grad else None
         grads = FrostingGrads(d_bary_logits=_p(d_bary), d_inner_verts=_p(d_in), d_outer_verts=_p(d_out),
@@ -70,13 +82,16 @@ class _FrostingAttributes(torch.autograd.Function):
             _lib.check(_lib.lib().fb200_frosting_attributes_backward(
                 C.byref(ctx.fp), _p(g_means3D), _p(g_opac), _p(g_scales), _p(g_rots), _p(g_shs), C.byref(grads),
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-        return (d_bary, d_op.view_as(opacity_logits), d_ls, d_q, d_dc, d_rest, d_in, d_out, None, None, None)
+        if ctx.sink is not None:
+            return (None, None, None, None, None, None, d_in, d_out, None, None, None, None)
+        return (d_bary, d_op.view_as(opacity_logits), d_ls, d_q, d_dc, d_rest, d_in, d_out, None, None, None, None)
 
 
-def frosting_attributes_fused(params, mesh, mask=None):
+def frosting_attributes_fused(params, mesh, mask=None, grad_sink=None):
     """params / mesh: the dicts of `scenes.frosting_layer` (bary_logits, opacity_logits, log_scales, quats, sh_dc,
-    sh_rest | inner, outer, cells, faces).  Returns the rasterizer inputs."""
+    sh_rest | inner, outer, cells, faces).  Returns the rasterizer inputs.  `grad_sink` (dict with the parameter
+    names): the backward writes the parameter gradients there (overwriting) instead of returning them to autograd."""
     means3D, opac, scales, rots, shs = _FrostingAttributes.apply(
         params["bary_logits"], params["opacity_logits"], params["log_scales"], params["quats"], params["sh_dc"],
-        params["sh_rest"], mesh["inner"], mesh["outer"], mesh["cells"], mesh["faces"], mask)
+        params["sh_rest"], mesh["inner"], mesh["outer"], mesh["cells"], mesh["faces"], mask, grad_sink)
     return dict(means3D=means3D, opacities=opac, scales=scales, rotations=rots, shs=shs)

@@ -1,0 +1,298 @@
+"""Data-parallel Adam for camera-sharded Frosting training -- host side.
+
+Mirrors the reference's optimizer wrapper (frosting_scene/frosting_optimizer.py): `OptimizationParams` carries the
+same defaults (:7-36), `FrostingAdam` exposes `step / zero_grad / update_learning_rate / state_dict` with the same
+group names and learning rates (:74-101) and the same two exponential schedules (:103-114, 123-134).  What is new is
+where the numbers live and how ranks exchange them:
+
+* all learnable tensors are views into ONE flat fp32 parameter slab, their gradients views into ONE gradient slab
+  (`FlatSlabs`); the fused attribute backward (`frosting_attributes_fused(..., grad_sink=opt.grads)`) writes straight
+  into the gradient slab, so there is no `.grad` accumulation pass;
+* under `torch.distributed` with world > 1 both slabs are peer-mapped (cudaIpc handles exchanged once through
+  `all_gather_object`) and `step()` launches `fb200_adam_step`: each rank reduces ITS 1/world shard of the gradients
+  out of all ranks' slabs over NVLink, updates its shard of the Adam moments, and stores the new parameters into
+  every rank's slab -- gradient all-reduce, optimizer and parameter broadcast in one kernel.  The two rendezvous it
+  needs are 4-byte NCCL all-reduces (the first one carries the scalar loss);
+* world == 1: the same kernel as a plain fused multi-group Adam.
+
+There is no CPU path: the slabs are CUDA memory and the step is the CUDA kernel.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class OptimizationParams:
+    """Same fields and defaults as frosting_scene/frosting_optimizer.py:7-36."""
+
+    def __init__(self, iterations=30_000, position_lr_init=0.00016, position_lr_final=0.0000016,
+                 position_bary_coords_lr_init=0.005, position_bary_coords_lr_final=0.00005,
+                 position_lr_delay_mult=0.01, position_lr_max_steps=30_000, feature_lr=0.0025, opacity_lr=0.05,
+                 scaling_lr=0.005, rotation_lr=0.001):
+        self.iterations = iterations
+        self.position_lr_init = position_lr_init
+        self.position_lr_final = position_lr_final
+        self.position_bary_coords_lr_init = position_bary_coords_lr_init
+        self.position_bary_coords_lr_final = position_bary_coords_lr_final
+        self.position_lr_delay_mult = position_lr_delay_mult
+        self.position_lr_max_steps = position_lr_max_steps
+        self.feature_lr = feature_lr
+        self.opacity_lr = opacity_lr
+        self.scaling_lr = scaling_lr
+        self.rotation_lr = rotation_lr
+
+
+def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """Log-linear interpolation lr_init -> lr_final over max_steps with an optional sine warm-up
+    (frosting_utils/general_utils.py:23-56)."""
+
+    def at(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        delay = 1.0
+        if lr_delay_steps > 0:
+            delay = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+        t = min(max(step / max_steps, 0), 1)
+        return delay * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+    return at
+
+
+# ---- slab layout (pure host logic; covered on CPU by tests/test_host_logic_cpu.py) ----
+
+def slab_layout(sizes, world=1):
+    """Element offsets of consecutive groups of `sizes` elements, each start rounded up to 4 elements (16 B), and the
+    padded total (a multiple of 4 * world so that equal shards are 4-aligned).  Returns (starts[len+1], total)."""
+    starts, at = [], 0
+    for n in sizes:
+        if n < 0:
+            raise ValueError("negative group size")
+        starts.append(at)
+        at += (int(n) + 3) // 4 * 4
+    quantum = 4 * max(int(world), 1)
+    total = (at + quantum - 1) // quantum * quantum
+    starts.append(at)
+    return starts, total
+
+
+def shard_range(total, rank, world):
+    """[lo, hi) of the flat slab owned by `rank`: equal 4-aligned shards (total is a multiple of 4 * world)."""
+    if total % (4 * world):
+        raise ValueError("total must be a multiple of 4 * world")
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    per = total // world
+    return rank * per, (rank + 1) * per
+
+
+class _DevicePointer:
+    """`__cuda_array_interface__` carrier so torch can view memory this library allocated."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr, n, device):
+    return torch.as_tensor(_DevicePointer(ptr, n), device=device)
+
+
+class FlatSlabs:
+    """Parameter and gradient slabs + named views.  `tensors`: ordered dict name -> initial CUDA tensor."""
+
+    def __init__(self, tensors, world=1, rank=0, peer=False, group=None):
+        names = list(tensors)
+        first = tensors[names[0]]
+        if not first.is_cuda:
+            raise RuntimeError("frosting_b200 optimizers keep their state in CUDA memory (no CPU fallback)")
+        self.device, self.names, self.world, self.rank, self.group = first.device, names, world, rank, group
+        self.shapes = {n: tuple(tensors[n].shape) for n in names}
+        self.starts, self.total = slab_layout([tensors[n].numel() for n in names], world)
+        self._owned, self._opened = [], []
+        L = _lib.lib()
+        if peer:
+            with torch.cuda.device(self.device):
+                ptrs = []
+                for _ in range(2):
+                    p = C.c_void_p()
+                    _lib.check(L.fb200_peer_alloc(self.total * 4, C.byref(p)))
+                    self._owned.append(p.value)
+                    ptrs.append(p.value)
+                self.param_slab = _view(ptrs[0], self.total, self.device)
+                self.grad_slab = _view(ptrs[1], self.total, self.device)
+                self.peer_params, self.peer_grads = self._exchange(L, ptrs)
+        else:
+            self.param_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self.grad_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self.peer_params, self.peer_grads = [self.param_slab.data_ptr()], [self.grad_slab.data_ptr()]
+        self.params, self.grads = {}, {}
+        for n, s in zip(names, self.starts):
+            k = tensors[n].numel()
+            self.param_slab[s:s + k].copy_(tensors[n].detach().reshape(-1).to(torch.float32))
+            self.params[n] = self.param_slab[s:s + k].view(self.shapes[n]).requires_grad_(True)
+            self.grads[n] = self.grad_slab[s:s + k].view(self.shapes[n])
+
+    def _exchange(self, L, ptrs):
+        """Trade cudaIpc handles with the other ranks of the box and map their slabs."""
+        mine = []
+        for p in ptrs:
+            h = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+            _lib.check(L.fb200_peer_export(C.c_void_p(p), h))
+            mine.append(h.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        out = ([], [])
+        for r, handles in enumerate(everyone):
+            for which, h in enumerate(handles):
+                if r == self.rank:
+                    out[which].append(ptrs[which])
+                    continue
+                q = C.c_void_p()
+                _lib.check(L.fb200_peer_open(h, C.byref(q)))
+                self._opened.append(q.value)
+                out[which].append(q.value)
+        return out
+
+    def close(self):
+        """Unmap peers and free the slabs (all ranks must have stopped using them: call after a barrier)."""
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for q in self._opened:
+                L.fb200_peer_close(C.c_void_p(q))
+            for p in self._owned:
+                L.fb200_peer_free(C.c_void_p(p))
+        self._opened, self._owned = [], []
+
+
+class FrostingAdam:
+    """Adam(lr per group, eps=1e-15) over flat slabs, data-parallel over the ranks of one box.
+
+    `tensors`: ordered dict name -> initial CUDA tensor; `lrs`: dict name -> learning rate.  After construction use
+    `opt.params[name]` as the learnable tensors (views into the parameter slab) and route gradients into
+    `opt.grads[name]` (views into the gradient slab; `frosting_attributes_fused(..., grad_sink=opt.grads)` does that
+    in its backward; `opt.collect_grads()` copies autograd's `.grad` there for any other producer)."""
+
+    def __init__(self, tensors, lrs, betas=(0.9, 0.999), eps=1e-15, group=None, average=True):
+        if len(tensors) > _lib.ADAM_MAX_GROUPS:
+            raise ValueError(f"at most {_lib.ADAM_MAX_GROUPS} parameter groups")
+        self.group = group
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError(f"at most {_lib.MAX_PEERS} ranks (one NVSwitch box)")
+        self.slabs = FlatSlabs(tensors, self.world, self.rank, peer=self.world > 1, group=group)
+        self.params, self.grads = self.slabs.params, self.slabs.grads
+        self.param_groups = [{"name": n, "lr": float(lrs[n]), "params": [self.params[n]]} for n in self.slabs.names]
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        self.grad_scale = 1.0 / self.world if average else 1.0
+        self.lo, self.hi = shard_range(self.slabs.total, self.rank, self.world)
+        dev = self.slabs.device
+        self.exp_avg = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=dev)
+        self.current_iteration = 0
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.position_sheduler_func = None
+        self.position_bary_coords_sheduler_func = None
+
+    # -- the reference's group list and schedules (frosting_optimizer.py:74-114) for the Frosting layer's tensors --
+    GROUP_OF = {"bary_logits": "bary_coords", "sh_dc": "sh_coordinates_dc", "sh_rest": "sh_coordinates_rest",
+                "opacity_logits": "opacities", "log_scales": "scales", "quats": "quaternions"}
+
+    @classmethod
+    def for_frosting(cls, params, opt=None, spatial_lr_scale=1.0, group=None):
+        opt = opt or OptimizationParams()
+        order = ("bary_logits", "sh_dc", "sh_rest", "opacity_logits", "log_scales", "quats")
+        lr = {"bary_logits": opt.position_bary_coords_lr_init, "sh_dc": opt.feature_lr, "sh_rest": opt.feature_lr / 20.0,
+              "opacity_logits": opt.opacity_lr, "log_scales": opt.scaling_lr, "quats": opt.rotation_lr}
+        self = cls({n: params[n] for n in order}, lr, eps=1e-15, group=group)
+        for g in self.param_groups:
+            g["name"] = cls.GROUP_OF[g["name"]]
+        self.num_iterations = opt.iterations
+        self.spatial_lr_scale = spatial_lr_scale
+        self.position_sheduler_func = get_expon_lr_func(opt.position_lr_init * spatial_lr_scale,
+                                                        opt.position_lr_final * spatial_lr_scale,
+                                                        lr_delay_mult=opt.position_lr_delay_mult,
+                                                        max_steps=opt.position_lr_max_steps)
+        self.position_bary_coords_sheduler_func = get_expon_lr_func(opt.position_bary_coords_lr_init,
+                                                                    opt.position_bary_coords_lr_final,
+                                                                    lr_delay_mult=opt.position_lr_delay_mult,
+                                                                    max_steps=opt.position_lr_max_steps)
+        return self
+
+    def update_learning_rate(self, iteration=None):
+        """frosting_optimizer.py:123-134."""
+        if iteration is None:
+            iteration = self.current_iteration
+        lr = 0.0
+        for g in self.param_groups:
+            if g["name"] in ("shell_base_verts", "inner_dist", "outer_dist", "bg_points") and self.position_sheduler_func:
+                lr = self.position_sheduler_func(iteration)
+                g["lr"] = lr
+            if g["name"] == "bary_coords" and self.position_bary_coords_sheduler_func:
+                lr = self.position_bary_coords_sheduler_func(iteration)
+                g["lr"] = lr
+        return lr
+
+    def zero_grad(self, set_to_none=True):
+        """Gradient producers overwrite the slab, so there is nothing to clear; `.grad` of the views is dropped."""
+        for p in self.params.values():
+            p.grad = None
+
+    def collect_grads(self):
+        """Copy autograd-populated `.grad`s into the gradient slab (for producers that do not take `grad_sink`)."""
+        for n, p in self.params.items():
+            if p.grad is not None:
+                self.grads[n].copy_(p.grad)
+
+    def _args(self):
+        t = self.current_iteration
+        a = _lib.AdamArgs()
+        a.world, a.rank = self.world, self.rank
+        for r in range(self.world):
+            a.peer_params[r] = self.slabs.peer_params[r]
+            a.peer_grads[r] = self.slabs.peer_grads[r]
+        a.d_exp_avg, a.d_exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.shard_lo, a.shard_hi = self.lo, self.hi
+        a.n_groups = len(self.param_groups)
+        for k, s in enumerate(self.slabs.starts[:-1]):
+            a.group_start[k] = s
+            a.lr[k] = self.param_groups[k]["lr"]
+        a.group_start[a.n_groups] = self.slabs.total
+        b1, b2 = self.betas
+        a.beta1, a.beta2, a.eps = b1, b2, self.eps
+        a.bias_correction1 = 1.0 - b1 ** t
+        a.bias_correction2_sqrt = math.sqrt(1.0 - b2 ** t)
+        a.grad_scale = self.grad_scale
+        return a
+
+    def step(self, loss=None):
+        """One optimizer step on the current stream.  `loss` (optional CUDA scalar): summed over ranks in place by the
+        first rendezvous, as the training loop's loss all-reduce."""
+        self.current_iteration += 1
+        dev = self.slabs.device
+        if self.world > 1:
+            # rendezvous 1: every rank's backward (its gradient slab) is complete before any shard is read
+            dist.all_reduce(loss if loss is not None else self._flag, group=self.group)
+        a = self._args()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fb200_adam_step(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if self.world > 1:
+            # rendezvous 2: every rank's parameter stores have landed before anyone's next forward
+            dist.all_reduce(self._flag, group=self.group)
+        return loss
+
+    def state_dict(self):
+        return {"step": self.current_iteration, "shard": (self.lo, self.hi), "exp_avg": self.exp_avg,
+                "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [{"name": g["name"], "lr": g["lr"]} for g in self.param_groups]}
+
+    def close(self):
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+        self.slabs.close()

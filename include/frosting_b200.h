@@ -202,6 +202,45 @@ int fb200_l1_dssim_forward(const float* d_pred, const float* d_gt, int32_t C, in
 int fb200_l1_dssim_backward(const float* d_pred, const float* d_gt, const float* d_maps, int32_t C, int32_t H,
                             int32_t W, float lambda, const float* d_dL_dloss, float* d_dpred, void* stream);
 
+/* Data-parallel gradient reduction fused with the Adam update.  Replaces "all-reduce every
+ * .grad, then torch.optim.Adam(l, lr=0.0, eps=1e-15).step()" (frosting_scene/frosting_optimizer.py:101,116-118) for
+ * camera-sharded training.  All learnable tensors of a rank live in ONE flat fp32 parameter slab and their gradients
+ * in ONE gradient slab of the same indexing; group g owns elements [group_start[g], group_start[g+1]) (starts are
+ * multiples of 4 elements) and has its own learning rate.  Rank `rank` owns elements [shard_lo, shard_hi) (multiples
+ * of 4): it sums that range of all `world` gradient slabs in rank order, scales by grad_scale, updates ITS moments
+ * (arrays of shard_hi - shard_lo elements) and stores the new parameters into all `world` parameter slabs.
+ * peer_params / peer_grads hold device pointers valid on THIS device (fb200_peer_open for the other ranks' slabs;
+ * entry `rank` is the local slab).  The caller orders the step after every rank's backward and orders the next
+ * forward after every rank's step (two stream-ordered rendezvous, e.g. 4-byte NCCL all-reduces).  world == 1: plain
+ * fused multi-group Adam.  bias_correction1 = 1 - beta1^t, bias_correction2_sqrt = sqrt(1 - beta2^t). */
+#define FB200_ADAM_MAX_GROUPS 16
+#define FB200_MAX_PEERS 8
+typedef struct fb200_adam_args {
+    int32_t world, rank;
+    float* peer_params[FB200_MAX_PEERS];
+    const float* peer_grads[FB200_MAX_PEERS];
+    float* d_exp_avg;
+    float* d_exp_avg_sq;
+    int64_t shard_lo, shard_hi;
+    int32_t n_groups;
+    int64_t group_start[FB200_ADAM_MAX_GROUPS + 1];
+    float lr[FB200_ADAM_MAX_GROUPS];
+    float beta1, beta2, eps;
+    float bias_correction1, bias_correction2_sqrt;
+    float grad_scale;
+} fb200_adam_args;
+int fb200_adam_step(const fb200_adam_args* args, void* stream);
+
+/* Peer-mapped slabs for fb200_adam_step (cudaMalloc + cudaIpc*; the only device allocations this library makes, and
+ * only on request).  fb200_peer_alloc zero-fills.  A handle is FB200_PEER_HANDLE_BYTES opaque bytes to be sent to the
+ * other ranks of the box (any host transport); fb200_peer_open maps that slab into the calling process. */
+#define FB200_PEER_HANDLE_BYTES 64
+int fb200_peer_alloc(size_t bytes, void** d_ptr);
+int fb200_peer_free(void* d_ptr);
+int fb200_peer_export(void* d_ptr, unsigned char* handle /* [FB200_PEER_HANDLE_BYTES] */);
+int fb200_peer_open(const unsigned char* handle, void** d_ptr);
+int fb200_peer_close(void* d_ptr);
+
 /* Introspection for parity tests: byte offsets of the internal arrays inside the caller's buffers,
  * so tests can compare depth bits / rects / records / ranges / point_list with the reference's
  * geomBuffer / binningBuffer / imgBuffer one-to-one. */

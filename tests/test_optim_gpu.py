@@ -1,0 +1,154 @@
+"""Row f3 on the GPU: fb200_adam_step against the numpy oracle and torch.optim.Adam, the grad_sink route of the fused
+attribute backward, and (when the box has >= 2 GPUs) the peer-memory data-parallel step under NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {"a": (1001, 6), "b": (1001, 1, 3), "c": (1001, 15, 3), "d": (1001, 1), "e": (333,), "f": (1001, 4)}
+LRS = {"a": 0.005, "b": 0.0025, "c": 0.000125, "d": 0.05, "e": 0.005, "f": 0.001}
+
+
+def _grads(t, rank, n):
+    rng = np.random.default_rng(1000 * t + rank)
+    g = rng.standard_normal(n).astype(np.float32) * (10.0 ** rng.integers(-6, 1, n)).astype(np.float32)
+    g[rng.random(n) < 0.3] = 0.0
+    return g
+
+
+def test_fused_adam_matches_oracle_and_torch():
+    from frosting_b200 import optim
+    from oracle import adam as adam_oracle
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    init = {n: rng.standard_normal(s).astype(np.float32) for n, s in SHAPES.items()}
+    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(dev) for n, x in init.items()}, LRS)
+    ref_p = {n: torch.from_numpy(x.copy()).to(dev).requires_grad_(True) for n, x in init.items()}
+    ref = torch.optim.Adam([{"params": [ref_p[n]], "lr": LRS[n]} for n in SHAPES], lr=0.0, eps=1e-15)
+    ora = {n: (init[n].reshape(-1).copy(), np.zeros(init[n].size, np.float32), np.zeros(init[n].size, np.float32))
+           for n in SHAPES}
+    before = __import__("frosting_b200")._lib.kernel_launches()
+    for t in range(1, 6):
+        for k, n in enumerate(SHAPES):
+            g = _grads(t, k, init[n].size)
+            opt.grads[n].copy_(torch.from_numpy(g).view(SHAPES[n]))
+            ref_p[n].grad = torch.from_numpy(g.copy()).view(SHAPES[n]).to(dev)
+            ora[n] = adam_oracle.adam_step(ora[n][0], g, ora[n][1], ora[n][2], LRS[n], t)
+        opt.step()
+        ref.step()
+    assert __import__("frosting_b200")._lib.kernel_launches() - before == 5       # one kernel per step, all groups
+    for n in SHAPES:
+        got = opt.params[n].detach().cpu().numpy().reshape(-1)
+        np.testing.assert_allclose(got, ora[n][0], rtol=3e-6, atol=1e-7)
+        np.testing.assert_allclose(got, ref_p[n].detach().cpu().numpy().reshape(-1), rtol=3e-6, atol=1e-7)
+    # the slab padding between groups stays zero
+    s = opt.slabs
+    mask = torch.ones(s.total, dtype=torch.bool, device=dev)
+    for n, st in zip(s.names, s.starts):
+        mask[st:st + init[n].size] = False
+    assert float(s.param_slab[mask].abs().max() if mask.any() else 0.0) == 0.0
+
+
+def test_adam_argument_checks():
+    import ctypes as C
+    from frosting_b200 import _lib
+    a = _lib.AdamArgs()
+    a.world, a.rank, a.n_groups = 1, 0, 1
+    a.group_start[0], a.group_start[1] = 0, 6          # not a multiple of 4
+    with pytest.raises(_lib.Fb200Error):
+        _lib.check(_lib.lib().fb200_adam_step(C.byref(a), None))
+    a.group_start[1] = 8
+    a.shard_lo, a.shard_hi = 0, 8                      # missing buffers
+    a.bias_correction1 = a.bias_correction2_sqrt = 1.0
+    with pytest.raises(_lib.Fb200Error):
+        _lib.check(_lib.lib().fb200_adam_step(C.byref(a), None))
+    a.world = 9
+    with pytest.raises(_lib.Fb200Error):
+        _lib.check(_lib.lib().fb200_adam_step(C.byref(a), None))
+
+
+def test_grad_sink_receives_the_autograd_gradients():
+    import frosting_b200 as fb
+    from frosting_b200 import scenes, optim
+    dev = torch.device("cuda:0")
+    P = 20_000
+    cam = scenes.make_camera(200, 120, device=dev)
+    params, mesh = scenes.frosting_layer(P, cam, 5, n_faces_target=4000, device=dev)
+    mask = (torch.rand(P, device=dev) < 0.7)
+    w = mask.float()
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    out = fb.frosting_attributes_fused(leaf, mesh, mask=mask)
+    cot = {k: torch.randn_like(v) for k, v in out.items()}
+    sum(((out[k] * cot[k]).reshape(P, -1).sum(1) * w).sum() for k in out).backward()
+    opt = optim.FrostingAdam.for_frosting(params)
+    out2 = fb.frosting_attributes_fused(opt.params, mesh, mask=mask, grad_sink=opt.grads)
+    sum(((out2[k] * cot[k]).reshape(P, -1).sum(1) * w).sum() for k in out2).backward()
+    for k in ("bary_logits", "opacity_logits", "log_scales", "quats", "sh_dc", "sh_rest"):
+        assert opt.params[k].grad is None
+        assert torch.equal(opt.grads[k].reshape(-1), leaf[k].grad.reshape(-1)), k
+    assert [g["name"] for g in opt.param_groups] == ["bary_coords", "sh_coordinates_dc", "sh_coordinates_rest",
+                                                     "opacities", "scales", "quaternions"]
+    opt.step()
+    assert opt.update_learning_rate(15_000) == pytest.approx(np.sqrt(0.005 * 0.00005))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _peer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from frosting_b200 import optim
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    rng = np.random.default_rng(3)
+    init = {n: rng.standard_normal(s).astype(np.float32) for n, s in SHAPES.items()}
+    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(dev) for n, x in init.items()}, LRS)
+    loss_sum = None
+    for t in range(1, 4):
+        for k, n in enumerate(SHAPES):
+            g = _grads(t, 10 * rank + k, init[n].size)
+            opt.grads[n].copy_(torch.from_numpy(g).view(SHAPES[n]))
+        loss = torch.tensor([float(rank + 1)], device=dev)
+        opt.step(loss=loss)
+        loss_sum = float(loss)
+    torch.cuda.synchronize(dev)
+    q.put((rank, {n: opt.params[n].detach().cpu().numpy().reshape(-1) for n in SHAPES}, loss_sum))
+    opt.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="peer-memory step needs 2 GPUs")
+def test_peer_memory_dp_adam_world2():
+    import torch.multiprocessing as mp
+    from oracle import adam as adam_oracle
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, params, loss_sum = q.get(timeout=300)
+        res[r] = params
+        assert loss_sum == 3.0
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    init = {n: rng.standard_normal(s).astype(np.float32) for n, s in SHAPES.items()}
+    for k, n in enumerate(SHAPES):
+        assert np.array_equal(res[0][n], res[1][n]), n          # replicas bit-identical
+        p, m, v = init[n].reshape(-1).copy(), np.zeros(init[n].size, np.float32), np.zeros(init[n].size, np.float32)
+        for t in range(1, 4):
+            gs = [_grads(t, 10 * r + k, init[n].size) for r in range(world)]
+            p, m, v = adam_oracle.dp_step(p, gs, m, v, LRS[n], t, 0.5)
+        np.testing.assert_allclose(res[0][n], p, rtol=3e-6, atol=1e-7)

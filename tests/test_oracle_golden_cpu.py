@@ -12,7 +12,7 @@ import torch
 from oracle import cpu
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("loss_"))
+              if not os.path.basename(p).startswith(("loss_", "adam")))
 
 
 def _settings(z):
