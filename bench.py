@@ -259,6 +259,61 @@ class ReferenceFrostingStep(ReferenceStep):
         return loss.detach()
 
 
+class OursDPTrainStep(OursFrostingStep):
+    """One data-parallel TRAINING iteration (row f3): every rank renders its camera from the shared parameters
+    (fused attributes -> mask -> rasterizer -> fused L1 + D-SSIM -> backward writing into the gradient slab), then ONE
+    kernel per rank reduces its shard of all ranks' gradients over NVLink peer memory, applies Adam (the reference's
+    groups / learning rates, frosting_optimizer.py:74-101) and stores the new parameters into every rank's slab."""
+    handles_collective = True
+
+    def __init__(self, wl, device):
+        super().__init__(wl, device)
+        self.opt = self.fb.FrostingAdam.for_frosting(wl["params"])
+        self.params = self.opt.params
+        self.real_loss = True
+
+    def __call__(self, i, rs, cot):
+        fb = self.fb
+        mask = fb.gaussian_render_mask(self.wl["face_visible"][i], self.wl["mesh"]["cells"], self.P)
+        a = fb.frosting_attributes_fused(self.params, self.wl["mesh"], mask, grad_sink=self.opt.grads)
+        means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
+        color, radii = fb.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=means2D, opacities=a["opacities"],
+                                                 shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
+                                                 visibility_mask=mask)
+        loss = fb.l1_dssim_loss(color, self.gt[i], 0.2)
+        loss.backward()
+        loss = loss.detach().reshape(1).clone()
+        self.opt.update_learning_rate()
+        self.opt.step(loss=loss)            # the loss all-reduce doubles as the pre-step rendezvous
+        return loss
+
+
+class ReferenceDPTrainStep(ReferenceFrostingStep):
+    """What a torch user gets from the reference today: its render chain, NCCL all-reduce of every .grad (averaged),
+    torch.optim.Adam(lr=0.0, eps=1e-15) over the same groups (frosting_optimizer.py:74-101,116-118)."""
+    handles_collective = True
+
+    def __init__(self, wl, device):
+        super().__init__(wl, device)
+        from frosting_b200.optim import OptimizationParams
+        o = OptimizationParams()
+        lr = {"bary_logits": o.position_bary_coords_lr_init, "sh_dc": o.feature_lr, "sh_rest": o.feature_lr / 20.0,
+              "opacity_logits": o.opacity_lr, "log_scales": o.scaling_lr, "quats": o.rotation_lr}
+        self.opt = torch.optim.Adam([{"params": [self.params[k]], "lr": lr[k], "name": k} for k in lr], lr=0.0, eps=1e-15)
+        self.real_loss = True
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def __call__(self, i, rs, cot):
+        loss = super().__call__(i, rs, cot).reshape(1).clone()
+        if self.world > 1:
+            dist.all_reduce(loss)
+            for v in self.params.values():
+                dist.all_reduce(v.grad)
+                v.grad.div_(self.world)
+        self.opt.step()
+        return loss
+
+
 def timed_loop(step, wl, device, steps, warmup, world, e2e):
     """Returns seconds for exactly `steps` steps (max over ranks)."""
     cams = wl["cams"]
@@ -298,7 +353,7 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
             else:
                 rs, cot = rs_dev[i], cot_dev[i]
             loss = step(i, rs, cot)
-            if world > 1:
+            if world > 1 and not getattr(step, "handles_collective", False):
                 dist.all_reduce(loss)                      # the path's only collective: scalar loss over NVLink
             if e2e:
                 # D2H read of the step's result, every step: async copy into pinned memory, consumed one step later so
@@ -454,7 +509,20 @@ def main():
         fstep.primed = False
         secs_t, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
         train_fps = world * args.steps / secs_t
+        gts = fstep.gt
         del fstep
+        # ... and as a data-parallel TRAINING iteration: gradient reduction over the ranks + Adam (row f3)
+        dp_fps = dp_err = None
+        try:
+            dstep = OursDPTrainStep(wl, device) if args.impl == "ours" else ReferenceDPTrainStep(wl, device)
+            dstep.gt = gts
+            secs_d, _, _ = timed_loop(dstep, wl, device, args.steps, args.warmup, world, e2e=False)
+            dp_fps = world * args.steps / secs_d
+            if args.impl == "ours":
+                dstep.opt.close()
+            del dstep
+        except Exception as ex:
+            dp_err = repr(ex)
     H, W, P = wl["H"], wl["W"], wl["P"]
     h2d = 3 * H * W * 4 + (16 + 16 + 3 + 3) * 4
     d2h = 4
@@ -485,6 +553,13 @@ def main():
         out["frosting_train_step"] = {"value": train_fps, "unit": UNIT,
                                       "note": "secondary: parameters -> attributes -> mask -> rasterizer -> 0.8 L1 + 0.2 (1-SSIM) "
                                               "-> backward (ours: fused loss kernel, row f2; reference: its torch loss)"}
+        if dp_fps is not None:
+            out["dp_train_step"] = {"value": dp_fps, "unit": UNIT,
+                                    "note": "secondary: one camera per rank per iteration, loss as above, then gradient mean over "
+                                            "the ranks + Adam with the reference's groups (ours: ONE peer-memory reduce+Adam+publish "
+                                            "kernel per rank, row f3; reference: NCCL all-reduce of each .grad + torch.optim.Adam)"}
+        else:
+            out["dp_train_step_error"] = dp_err
     if clocks:
         out["clocks"] = clocks
     if args.impl == "reference":

@@ -24,6 +24,7 @@ EXPORTED = [
     "fb200_adam_step", "fb200_peer_alloc", "fb200_peer_free", "fb200_peer_export", "fb200_peer_open", "fb200_peer_close",
 ]
 NUM_STAGES = 5
+ABI_VERSION = 2
 STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
 
 
@@ -33,7 +34,13 @@ class Params(C.Structure):
         ("image_width", C.c_int32), ("image_height", C.c_int32),
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("extra", C.c_void_p),          # const fb200_extra* (row f4) or NULL
     ]
+
+
+class Extra(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("d_features", C.c_void_p), ("d_background", C.c_void_p),
+                ("d_out", C.c_void_p), ("d_dL_dout", C.c_void_p), ("d_dL_dfeatures", C.c_void_p)]
 
 
 class Inputs(C.Structure):
@@ -81,7 +88,7 @@ class AdamArgs(C.Structure):
                 ("d_exp_avg", C.c_void_p), ("d_exp_avg_sq", C.c_void_p),
                 ("shard_lo", C.c_int64), ("shard_hi", C.c_int64), ("n_groups", C.c_int32),
                 ("group_start", C.c_int64 * (ADAM_MAX_GROUPS + 1)), ("lr", C.c_float * ADAM_MAX_GROUPS),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_float),
                 ("bias_correction1", C.c_float), ("bias_correction2_sqrt", C.c_float), ("grad_scale", C.c_float)]
 
 
@@ -164,7 +171,7 @@ def lib():
     for n in ("fb200_forward", "fb200_forward_geometry", "fb200_forward_raster", "fb200_backward", "fb200_mark_visible", "fb200_mesh_visibility",
               "fb200_gaussian_mask_from_faces", "fb200_get_layout"):
         getattr(L, n).restype = C.c_int
-    if L.fb200_abi_version() != 1:
+    if L.fb200_abi_version() != ABI_VERSION:
         raise RuntimeError("frosting_b200: ABI version mismatch between header and library")
     _lib = L
     return L

@@ -73,6 +73,21 @@ int validate(const fb200_params* prm, const fb200_inputs* in, const fb200_worksp
     return FB200_OK;
 }
 
+// row f4: copy the caller's extra-channel block into kernel arguments
+int setup_extra(const fb200_params* prm, bool forward, bool backward, ExtraArgs& ex) {
+    memset(&ex, 0, sizeof(ex));
+    const fb200_extra* e = prm->extra;
+    if (!e || prm->P == 0) return FB200_OK;
+    if (e->channels < 1 || e->channels > FB200_CHANNELS)
+        return fail(FB200_EINVAL, "extra feature channels must be 1..3%s");
+    if (!e->d_features || !e->d_background) return fail(FB200_EINVAL, "extra features / background missing%s");
+    if (forward && !e->d_out) return fail(FB200_EINVAL, "extra output image missing%s");
+    if (backward && (!e->d_dL_dout || !e->d_dL_dfeatures)) return fail(FB200_EINVAL, "extra gradient pointers missing%s");
+    ex.ch = e->channels; ex.feat = e->d_features; ex.bg = e->d_background; ex.out = e->d_out;
+    ex.dL_dout = e->d_dL_dout; ex.dL_dfeat = e->d_dL_dfeatures;
+    return FB200_OK;
+}
+
 // ---- measurement hooks -------------------------------------------------------------------------------
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_profile{0};
@@ -216,6 +231,7 @@ int fb200_forward_raster(const fb200_params* prm, const fb200_inputs* in, const 
     FwdArgs a;
     int rc = setup_fwd(prm, in, ws, true, d_out_color, d_radii, a);
     if (rc != FB200_OK) return rc;
+    if ((rc = setup_extra(prm, true, false, a.ex)) != FB200_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool debug = (prm->debug & 1) != 0;
     { StageTimer t(FB200_STAGE_BINNING, s);
@@ -270,12 +286,14 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     a.radii = d_radii;
     a.dL_dpix = d_dL_dout_color;
     a.g = *grads;
+    if ((rc = setup_extra(prm, false, true, a.ex)) != FB200_OK) return rc;
 
     if ((rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
     { StageTimer t(FB200_STAGE_RENDER_BWD, s);
       if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc; }
     { StageTimer t(FB200_STAGE_GEOM_BWD, s);
       if ((rc = stage(launch_geom_bwd(a, s), "geometry backward", debug, s)) != FB200_OK) return rc; }
+    if ((rc = stage(launch_extra_grad(a, s), "extra feature gradients", debug, s)) != FB200_OK) return rc;
     return FB200_OK;
 }
 

@@ -30,28 +30,37 @@ namespace {
 
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcg(p); }   // L2 only: peer data is never L1-cached
 
-__device__ __forceinline__ float adam1(float g, float& m, float& v, float p, float lr_over_bc1, const fb200_adam_args& a) {
-    m = m + (g - m) * (1.0f - a.beta1);
-    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
-    const float denom = sqrtf(v) / a.bias_correction2_sqrt + a.eps;
+struct Coef {
+    float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps;
+};
+
+__device__ __forceinline__ float adam1(float g, float& m, float& v, float p, float lr_over_bc1, const Coef& c) {
+    m = m + (g - m) * c.one_minus_b1;
+    v = v * c.b2 + c.one_minus_b2 * g * g;
+    const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
     return p - lr_over_bc1 * (m / denom);
 }
 
-__global__ void __launch_bounds__(256)
+// kPeers: compile-time bound on `world` (1, 2, 4, 8) so that small boxes do not pay registers for eight gradient
+// vectors -- more resident warps = more remote loads in flight, which is what hides the NVLink latency
+template <int kPeers>
+__global__ void __launch_bounds__(256, kPeers <= 4 ? 4 : 3)
 adam_shard_kernel(const fb200_adam_args a) {
     const int64_t v_lo = a.shard_lo >> 2, v_hi = a.shard_hi >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float4* __restrict__ mom1 = reinterpret_cast<float4*>(a.d_exp_avg);
     float4* __restrict__ mom2 = reinterpret_cast<float4*>(a.d_exp_avg_sq);
+    // torch forms 1 - beta in double and rounds once (python floats); (float)1 - (float)beta would be off by 1e-5 relative
+    const Coef c{(float)(1.0 - a.beta1), (float)a.beta2, (float)(1.0 - a.beta2), a.bias_correction2_sqrt, a.eps};
     for (int64_t i = v_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v_hi; i += stride) {
         // gradient: one 128-bit load per peer, all issued before the first use
-        float4 g[FB200_MAX_PEERS];
+        float4 g[kPeers];
 #pragma unroll
-        for (int p = 0; p < FB200_MAX_PEERS; ++p)
+        for (int p = 0; p < kPeers; ++p)
             if (p < a.world) g[p] = ld_stream(reinterpret_cast<const float4*>(a.peer_grads[p]) + i);
         float4 s = g[0];
 #pragma unroll
-        for (int p = 1; p < FB200_MAX_PEERS; ++p)
+        for (int p = 1; p < kPeers; ++p)
             if (p < a.world) { s.x += g[p].x; s.y += g[p].y; s.z += g[p].z; s.w += g[p].w; }
         s.x *= a.grad_scale; s.y *= a.grad_scale; s.z *= a.grad_scale; s.w *= a.grad_scale;
 
@@ -66,14 +75,14 @@ adam_shard_kernel(const fb200_adam_args a) {
         const int64_t li = i - v_lo;
         float4 m = mom1[li], v = mom2[li];
         float4 p = reinterpret_cast<const float4*>(a.peer_params[a.rank])[i];
-        p.x = adam1(s.x, m.x, v.x, p.x, step, a);
-        p.y = adam1(s.y, m.y, v.y, p.y, step, a);
-        p.z = adam1(s.z, m.z, v.z, p.z, step, a);
-        p.w = adam1(s.w, m.w, v.w, p.w, step, a);
+        p.x = adam1(s.x, m.x, v.x, p.x, step, c);
+        p.y = adam1(s.y, m.y, v.y, p.y, step, c);
+        p.z = adam1(s.z, m.z, v.z, p.z, step, c);
+        p.w = adam1(s.w, m.w, v.w, p.w, step, c);
         mom1[li] = m;
         mom2[li] = v;
 #pragma unroll
-        for (int q = 0; q < FB200_MAX_PEERS; ++q)
+        for (int q = 0; q < kPeers; ++q)
             if (q < a.world) __stcg(reinterpret_cast<float4*>(a.peer_params[q]) + i, p);
     }
 }
@@ -88,7 +97,10 @@ cudaError_t launch_adam_shard(const fb200_adam_args& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (vecs + 255) / 256;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);   // 8 resident CTAs of 256 threads per SM
-    adam_shard_kernel<<<grid, 256, 0, s>>>(a);
+    if (a.world == 1) adam_shard_kernel<1><<<grid, 256, 0, s>>>(a);
+    else if (a.world == 2) adam_shard_kernel<2><<<grid, 256, 0, s>>>(a);
+    else if (a.world <= 4) adam_shard_kernel<4><<<grid, 256, 0, s>>>(a);
+    else adam_shard_kernel<8><<<grid, 256, 0, s>>>(a);
     count_launch();
     return cudaGetLastError();
 }

@@ -87,11 +87,11 @@ def _f32c(t: torch.Tensor, device, name: str) -> torch.Tensor:
 class _Call:
     """Everything one forward needs again in backward (kept alive by the autograd ctx)."""
     __slots__ = ("prm", "inp", "ws", "tensors", "geom", "image", "binning", "status", "capacity",
-                 "num_rendered", "device")
+                 "num_rendered", "device", "extra")
 
 
 def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    rs: GaussianRasterizationSettings, visibility):
+                    rs: GaussianRasterizationSettings, visibility, extra_features=None, extra_bg=None):
     L = _lib.lib()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:57-59
@@ -121,10 +121,22 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
 
     M = sh.size(1) if sh.numel() != 0 else 0   # rasterize_points.cu:84-87
 
+    # row f4: extra feature channels blended in the same traversal
+    extra = None
+    if extra_features is not None:
+        extra_features = _f32c(extra_features, device, "extra_features")
+        if extra_features.dim() != 2 or extra_features.size(0) != P or not (1 <= extra_features.size(1) <= 3):
+            raise RuntimeError("extra_features must have dimensions (num_points, 1..3)")
+        E = extra_features.size(1)
+        extra_bg = torch.zeros(E, dtype=torch.float32, device=device) if extra_bg is None \
+            else _f32c(extra_bg.reshape(-1), device, "extra_background")
+        if extra_bg.numel() != E:
+            raise RuntimeError("extra_background must have one value per extra channel")
+
     prm = Params(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=int(M), image_width=W, image_height=H,
                  tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
                  scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
-                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0))
+                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0), extra=None)
     inp = Inputs(d_background=_ptr(bg), d_means3D=_ptr(means3D), d_shs=_ptr(sh),
                  d_colors_precomp=_ptr(colors_precomp), d_opacities=_ptr(opacities), d_scales=_ptr(scales),
                  d_rotations=_ptr(rotations), d_cov3D_precomp=_ptr(cov3Ds_precomp),
@@ -134,6 +146,14 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
         stream = torch.cuda.current_stream(device)
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         radii = torch.empty((P,), dtype=torch.int32, device=device)
+        out_extra = None
+        if extra_features is not None:
+            out_extra = torch.empty((extra_features.size(1), H, W), dtype=torch.float32, device=device)
+            if P == 0:
+                out_extra.copy_(extra_bg.view(-1, 1, 1).expand_as(out_extra))
+            extra = _lib.Extra(channels=extra_features.size(1), d_features=_ptr(extra_features),
+                               d_background=_ptr(extra_bg), d_out=_ptr(out_extra), d_dL_dout=None, d_dL_dfeatures=None)
+            prm.extra = C.addressof(extra)
         gb, ib = _sizes(L, P, W, H)
         slab = torch.empty((gb + ib + 128,), dtype=torch.uint8, device=device)   # one allocator call
         geom, image = slab[:gb], slab[gb:gb + ib]
@@ -163,13 +183,14 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
     call = _Call()
     call.prm, call.inp, call.ws = prm, inp, ws
     call.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, view, proj,
-                    campos, vis)
+                    campos, vis, extra_features, extra_bg)
+    call.extra = extra
     call.geom, call.image, call.binning, call.status = geom, image, binning, status
     call.capacity, call.num_rendered, call.device = capacity, num_rendered, device
-    return out_color, radii, call
+    return out_color, radii, call, out_extra
 
 
-def _launch_backward(call: "_Call", radii, grad_out_color):
+def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None):
     L = _lib.lib()
     prm = call.prm
     P, M = prm.P, prm.sh_coeffs
@@ -191,6 +212,15 @@ def _launch_backward(call: "_Call", radii, grad_out_color):
         dL_dmeans3D, dL_dmeans2D, dL_dcolors = cut(0, (P, 3)), cut(1, (P, 3)), cut(2, (P, 3))
         dL_dopacity, dL_dcov3D, dL_dsh = cut(3, (P, 1)), cut(4, (P, 6)), cut(5, (P, M, 3))
         dL_dscales, dL_drotations = cut(6, (P, 3)), cut(7, (P, 4))
+        dL_dextra = None
+        if call.extra is not None:
+            E = call.extra.channels
+            ge = grad_out_extra
+            ge = torch.zeros((E, prm.image_height, prm.image_width), dtype=torch.float32, device=device) if ge is None \
+                else ge.float().contiguous()
+            dL_dextra = torch.empty((P, E), dtype=torch.float32, device=device)
+            call.extra.d_dL_dout, call.extra.d_dL_dfeatures = ge.data_ptr(), dL_dextra.data_ptr()
+            prm.extra = C.addressof(call.extra)
         grads = Grads(d_dL_dmeans2D=_ptr(dL_dmeans2D), d_dL_dcolors=_ptr(dL_dcolors),
                       d_dL_dopacity=_ptr(dL_dopacity), d_dL_dmeans3D=_ptr(dL_dmeans3D),
                       d_dL_dcov3D=_ptr(dL_dcov3D), d_dL_dsh=_ptr(dL_dsh), d_dL_dscales=_ptr(dL_dscales),
@@ -199,7 +229,7 @@ def _launch_backward(call: "_Call", radii, grad_out_color):
                                     C.c_void_p(radii.data_ptr()) if P > 0 else None,
                                     C.c_void_p(g.data_ptr()), C.byref(grads),
                                     C.c_void_p(stream.cuda_stream)))
-    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dextra
 
 
 def last_num_rendered() -> int:
@@ -212,50 +242,53 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, visibility_mask=None):
-    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, visibility_mask)
+                        raster_settings, visibility_mask=None, extra_features=None, extra_background=None):
+    out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                    cov3Ds_precomp, raster_settings, visibility_mask, extra_features, extra_background)
+    return out if extra_features is not None else out[:2]
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, visibility_mask=None):
+                raster_settings, visibility_mask=None, extra_features=None, extra_background=None):
         args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-                visibility_mask)
+                visibility_mask, extra_features, extra_background)
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args[:7])   # copy before they can be corrupted
             try:
-                color, radii, call = _launch_forward(*args)
+                color, radii, call, extra = _launch_forward(*args)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            color, radii, call = _launch_forward(*args)
+            color, radii, call, extra = _launch_forward(*args)
         ctx.call = call
         ctx.num_rendered = call.num_rendered
         ctx.raster_settings = raster_settings
         ctx.present = tuple(t.numel() != 0 for t in (sh, colors_precomp, scales, rotations, cov3Ds_precomp))
         ctx.save_for_backward(radii)
         ctx.mark_non_differentiable(radii)
-        return color, radii
+        if extra is None:
+            extra = color.new_empty(0)        # placeholder third output (autograd wants tensors)
+        return color, radii, extra
 
     @staticmethod
-    def backward(ctx, grad_out_color, _):
+    def backward(ctx, grad_out_color, _, grad_out_extra=None):
         (radii,) = ctx.saved_tensors
         call = ctx.call
         if ctx.raster_settings.debug:
             try:
-                out = _launch_backward(call, radii, grad_out_color)
+                out = _launch_backward(call, radii, grad_out_color, grad_out_extra)
             except Exception as ex:
                 torch.save(cpu_deep_copy_tuple(call.tensors[:7]) + (grad_out_color.cpu().clone(),), "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            out = _launch_backward(call, radii, grad_out_color)
+            out = _launch_backward(call, radii, grad_out_color, grad_out_extra)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
-         grad_scales, grad_rotations) = out
+         grad_scales, grad_rotations, grad_extra) = out
         has_sh, has_col, has_s, has_r, has_cov = ctx.present
         # same order as DGR/diff_gaussian_rasterization/__init__.py:143-153
         return (
@@ -268,6 +301,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_rotations if has_r else None,
             grad_cov3Ds_precomp if has_cov else None,
             None,
+            None,
+            grad_extra,
             None,
         )
 
@@ -296,7 +331,11 @@ class GaussianRasterizer(nn.Module):
         return present
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, visibility_mask=None):
+                cov3D_precomp=None, visibility_mask=None, extra_features=None, extra_background=None):
+        """Reference surface (`__init__.py:187-220`) plus two opt-in extensions: `visibility_mask` (row a19) and
+        `extra_features` [P, 1..3] (row f4) -- blended with the colour's weights in the same traversal; when given, a
+        third output `[E, H, W]` is returned (what a second call with `colors_precomp=extra_features` and
+        `bg=extra_background` would return, sugar_model.py:2343-2387)."""
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -318,7 +357,7 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, raster_settings, visibility_mask)
+                                   cov3D_precomp, raster_settings, visibility_mask, extra_features, extra_background)
 
 
 # ---- introspection for parity tests ----------------------------------------------------------------------
@@ -328,7 +367,7 @@ def forward_with_state(raster_settings, means3D, opacities, shs=None, colors_pre
     bits, rects, records, ranges and the sorted point list with the reference's buffers."""
     e = torch.Tensor([])
     with torch.no_grad():
-        color, radii, call = _launch_forward(
+        color, radii, call, _ = _launch_forward(
             means3D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
             e if scales is None else scales, e if rotations is None else rotations,
             e if cov3D_precomp is None else cov3D_precomp, raster_settings, visibility_mask)

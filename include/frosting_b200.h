@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 1
+#define FB200_ABI_VERSION 2
 
 #define FB200_OK 0
 #define FB200_EINVAL (-1)   /* bad argument (shape / null pointer / unsupported channel count) */
@@ -44,6 +44,21 @@ extern "C" {
 
 #define FB200_TILE 16       /* tile edge in pixels: BLOCK_X/BLOCK_Y, DGR/cuda_rasterizer/config.h:16-17 */
 #define FB200_CHANNELS 3    /* NUM_CHANNELS, DGR/cuda_rasterizer/config.h:15 */
+
+/* Extra per-Gaussian feature channels blended with the same weights as the colour, in the same traversal (SURVEY.md
+ * row f4).  The reference obtains depth / normal maps by calling the 3-channel rasterizer AGAIN with the features as
+ * colors_precomp (frosting_scene/sugar_model.py:2343-2387, coarse_density_and_dn_consistency.py:649,689-714): a second
+ * preprocess + sort + blend over the same geometry.  Here: out[c] = sum_i f_i[c] alpha_i T_i + T_final background[c],
+ * i.e. exactly what that second pass returns, and the backward adds the features' contribution to dL/dalpha (hence to
+ * the geometry gradients) -- the sum of the two passes' gradients. */
+typedef struct fb200_extra {
+    int32_t channels;             /* 1..3 */
+    const float* d_features;      /* [P, channels] */
+    const float* d_background;    /* [channels] */
+    float* d_out;                 /* [channels, H, W]  written by fb200_forward_raster */
+    const float* d_dL_dout;       /* [channels, H, W]  read by fb200_backward */
+    float* d_dL_dfeatures;        /* [P, channels]     written by fb200_backward (fully) */
+} fb200_extra;
 
 /* Per-call scalars: the non-tensor fields of GaussianRasterizationSettings
  * (DGR/diff_gaussian_rasterization/__init__.py:157-169) plus the tensor extents. */
@@ -58,6 +73,7 @@ typedef struct fb200_params {
     float scale_modifier;
     int32_t prefiltered;     /* trap if a Gaussian is near-culled (auxiliary.h:156-160) */
     int32_t debug;           /* synchronise + check after every stage */
+    const fb200_extra* extra; /* NULL: colour only (the reference's surface) */
 } fb200_params;
 
 /* Device inputs of the forward pass.  Exactly one of (d_shs | d_colors_precomp) and exactly one of
@@ -225,7 +241,8 @@ typedef struct fb200_adam_args {
     int32_t n_groups;
     int64_t group_start[FB200_ADAM_MAX_GROUPS + 1];
     float lr[FB200_ADAM_MAX_GROUPS];
-    float beta1, beta2, eps;
+    double beta1, beta2;   /* double: 1 - beta is formed in double like torch does, then rounded to fp32 */
+    float eps;
     float bias_correction1, bias_correction2_sqrt;
     float grad_scale;
 } fb200_adam_args;

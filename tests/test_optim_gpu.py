@@ -43,8 +43,8 @@ def test_fused_adam_matches_oracle_and_torch():
     assert __import__("frosting_b200")._lib.kernel_launches() - before == 5       # one kernel per step, all groups
     for n in SHAPES:
         got = opt.params[n].detach().cpu().numpy().reshape(-1)
-        np.testing.assert_allclose(got, ora[n][0], rtol=3e-6, atol=1e-7)
-        np.testing.assert_allclose(got, ref_p[n].detach().cpu().numpy().reshape(-1), rtol=3e-6, atol=1e-7)
+        np.testing.assert_allclose(got, ora[n][0], rtol=3e-6, atol=5e-7)
+        np.testing.assert_allclose(got, ref_p[n].detach().cpu().numpy().reshape(-1), rtol=3e-6, atol=5e-7)
     # the slab padding between groups stays zero
     s = opt.slabs
     mask = torch.ones(s.total, dtype=torch.bool, device=dev)
@@ -151,4 +151,4 @@ def test_peer_memory_dp_adam_world2():
         for t in range(1, 4):
             gs = [_grads(t, 10 * r + k, init[n].size) for r in range(world)]
             p, m, v = adam_oracle.dp_step(p, gs, m, v, LRS[n], t, 0.5)
-        np.testing.assert_allclose(res[0][n], p, rtol=3e-6, atol=1e-7)
+        np.testing.assert_allclose(res[0][n], p, rtol=3e-6, atol=5e-7)
