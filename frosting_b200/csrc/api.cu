@@ -253,9 +253,12 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     int rc = validate(prm, in, ws);
     if (rc != FB200_OK) return rc;
     if (!grads || !d_dL_dout_color || (prm->P > 0 && !d_radii)) return fail(FB200_EINVAL, "backward pointers missing%s");
-    if (prm->P > 0 && (!grads->d_dL_dmeans2D || !grads->d_dL_dcolors || !grads->d_dL_dopacity ||
-                       !grads->d_dL_dmeans3D || !grads->d_dL_dcov3D || !grads->d_dL_dscales ||
-                       !grads->d_dL_drotations || (prm->sh_coeffs > 0 && !grads->d_dL_dsh)))
+    // outputs a caller cannot use may be NULL and are then not written: dL/dcolors on the SH path (an intermediate
+    // there), dL/dcov3D on the scale/rotation path, dL/dscales + dL/drotations on the precomputed-covariance path
+    if (prm->P > 0 && (!grads->d_dL_dmeans2D || !grads->d_dL_dopacity || !grads->d_dL_dmeans3D ||
+                       (in->d_colors_precomp && !grads->d_dL_dcolors) || (in->d_cov3D_precomp && !grads->d_dL_dcov3D) ||
+                       (!in->d_cov3D_precomp && (!grads->d_dL_dscales || !grads->d_dL_drotations)) ||
+                       (in->d_shs && prm->sh_coeffs > 0 && !grads->d_dL_dsh)))
         return fail(FB200_EINVAL, "gradient output pointers missing%s");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool debug = (prm->debug & 1) != 0;

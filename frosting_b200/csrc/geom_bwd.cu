@@ -75,12 +75,12 @@ geom_bwd_kernel(BwdArgs a) {
     if (full_warp && !__any_sync(0xffffffffu, visible)) {
         const size_t g = (size_t)g0;
         warp_zero4(a.g.d_dL_dmeans2D + 3 * g, 24, lane);
-        warp_zero4(a.g.d_dL_dcolors + 3 * g, 24, lane);
+        if (a.g.d_dL_dcolors) warp_zero4(a.g.d_dL_dcolors + 3 * g, 24, lane);
         warp_zero4(a.g.d_dL_dopacity + g, 8, lane);
         warp_zero4(a.g.d_dL_dmeans3D + 3 * g, 24, lane);
-        warp_zero4(a.g.d_dL_dcov3D + 6 * g, 48, lane);
-        warp_zero4(a.g.d_dL_dscales + 3 * g, 24, lane);
-        warp_zero4(a.g.d_dL_drotations + 4 * g, 32, lane);
+        if (a.g.d_dL_dcov3D) warp_zero4(a.g.d_dL_dcov3D + 6 * g, 48, lane);
+        if (a.g.d_dL_dscales) warp_zero4(a.g.d_dL_dscales + 3 * g, 24, lane);
+        if (a.g.d_dL_drotations) warp_zero4(a.g.d_dL_drotations + 4 * g, 32, lane);
         if (a.g.d_dL_dsh != nullptr && M > 0 && ((M * 3) & 3) == 0) warp_zero4(a.g.d_dL_dsh + (size_t)M * 3 * g, M * 24, lane);
         else if (a.g.d_dL_dsh != nullptr && M > 0)
             for (int k = lane; k < M * 3 * 32; k += 32) a.g.d_dL_dsh[(size_t)M * 3 * g + k] = 0.f;
@@ -335,12 +335,13 @@ geom_bwd_kernel(BwdArgs a) {
     if (!in_range) return;
 
     a.g.d_dL_dmeans2D[3 * i] = g_mean2d_x; a.g.d_dL_dmeans2D[3 * i + 1] = g_mean2d_y; a.g.d_dL_dmeans2D[3 * i + 2] = 0.f;
-    a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z;
+    if (a.g.d_dL_dcolors) { a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z; }
     a.g.d_dL_dopacity[i] = g_op;
     a.g.d_dL_dmeans3D[3 * i] = g_mean.x; a.g.d_dL_dmeans3D[3 * i + 1] = g_mean.y; a.g.d_dL_dmeans3D[3 * i + 2] = g_mean.z;
-    for (int k = 0; k < 6; ++k) a.g.d_dL_dcov3D[6 * i + k] = g_cov[k];
-    a.g.d_dL_dscales[3 * i] = g_scale.x; a.g.d_dL_dscales[3 * i + 1] = g_scale.y; a.g.d_dL_dscales[3 * i + 2] = g_scale.z;
-    reinterpret_cast<float4*>(a.g.d_dL_drotations)[i] = g_rot;
+    if (a.g.d_dL_dcov3D)
+        for (int k = 0; k < 6; ++k) a.g.d_dL_dcov3D[6 * i + k] = g_cov[k];
+    if (a.g.d_dL_dscales) { a.g.d_dL_dscales[3 * i] = g_scale.x; a.g.d_dL_dscales[3 * i + 1] = g_scale.y; a.g.d_dL_dscales[3 * i + 2] = g_scale.z; }
+    if (a.g.d_dL_drotations) reinterpret_cast<float4*>(a.g.d_dL_drotations)[i] = g_rot;
 }
 
 }  // namespace

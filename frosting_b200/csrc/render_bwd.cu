@@ -13,6 +13,8 @@
 //     tile are L1/L2 hits;
 //   * the same conservative alpha>=1/255 extents as the forward kernel let a warp skip instances
 //     that cannot touch its sub-tile.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fb200 {
@@ -306,6 +308,309 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     }
 }
 
+
+// ---- v3: two Gaussians per lane-iteration with packed fp32 ---------------------------------------------------------
+// The per-warp hit records of a step are COMPACTED into a structure-of-arrays slab (slot = rank of the lane among the
+// hits), so hits 2k and 2k+1 sit in adjacent words and one 64-bit shared load yields an aligned register pair; the
+// alpha evaluation (libdevice-exact exp included) and the gradient algebra then run as FFMA2/FMUL2/FADD2 on
+// (Gaussian 2k, Gaussian 2k+1).  Only the transmittance / accum_rec recurrences, which chain through the two
+// Gaussians at a pixel, stay scalar.  The 18 partial gradients (2 x 9) of the pair are summed over the warp by ONE
+// transposing butterfly -- 16 values fold 16->8->4->2->1 over lane bits 4..1, the two blue-channel values ride along --
+// in 20 shuffles, and ONE red.global.add instruction (18 lanes) retires both Gaussians.
+struct __align__(16) PairSlab {
+    float x[34], y[34], A[34], B[34], C[34], op[34], r[34], g[34], b[34];
+    uint32_t id[34], pos[34];
+};
+struct __align__(16) PairSlabX {
+    float e0[34], e1[34], e2[34];
+};
+
+__device__ __forceinline__ P2 ldp(const float* a, int k) { return *reinterpret_cast<const float2*>(a + k); }
+
+template <bool kExtra>
+__global__ void __launch_bounds__(256, kExtra ? 2 : 3)
+render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                       const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
+                       const float* __restrict__ bg, const float* __restrict__ final_T,
+                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
+                       float* __restrict__ acc, const int32_t* __restrict__ status, const ExtraArgs ex) {
+    __shared__ PairSlab slabs[kWarpsPerTile];
+    __shared__ PairSlabX slabs_x[kExtra ? kWarpsPerTile : 1];
+    if (status[FB200_ST_OVERFLOW]) return;
+
+    const unsigned full = 0xffffffffu;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5;
+    int lane;
+    unsigned lt_mask;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    const bool lb4 = lane & 16, lb3 = lane & 8, lb2 = lane & 4, lb1 = lane & 2, lb0 = lane & 1;
+    // after the butterfly: even lanes hold value (lane >> 1) & 7 of Gaussian (lane >> 4); odd lanes hold the ride-along
+    // values: slot 8 (kExtra: 8 + ((lane >> 2) & 3)) of Gaussian (lane >> 4)
+    const bool red_lane = !lb0 || (kExtra ? (lane & 3) == 1 : (lane & 15) == 1);
+    const int red_slot = lb0 ? (kExtra ? 8 + ((lane >> 2) & 3) : 8) : ((lane >> 1) & 7);
+    PairSlab& slab = slabs[warp];
+    PairSlabX& slabx = slabs_x[kExtra ? warp : 0];
+    const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
+    const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
+    const int pix_x = sub_x0 + (lane & 7), pix_y = sub_y0 + (lane >> 3);
+    const bool inside = pix_x < W && pix_y < H;
+    const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float lox = (float)sub_x0, hix = (float)(sub_x0 + kSubW - 1);
+    const float loy = (float)sub_y0, hiy = (float)(sub_y0 + kSubH - 1);
+    const size_t pix_id = (size_t)pix_y * W + pix_x;
+    const size_t HW = (size_t)H * W;
+
+    const uint2 range = ranges[tile];
+
+    const float T_final = inside ? final_T[pix_id] : 0.f;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    if (inside) {
+        dp0 = dL_dpix[pix_id];
+        dp1 = dL_dpix[HW + pix_id];
+        dp2 = dL_dpix[2 * HW + pix_id];
+    }
+    float bg_dot_dpixel = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    float de0 = 0.f, de1 = 0.f, de2 = 0.f;
+    if (kExtra) {
+        if (inside) {
+            de0 = ex.dL_dout[pix_id];
+            if (ex.ch > 1) de1 = ex.dL_dout[HW + pix_id];
+            if (ex.ch > 2) de2 = ex.dL_dout[2 * HW + pix_id];
+        }
+        bg_dot_dpixel += ex.bg[0] * de0;
+        if (ex.ch > 1) bg_dot_dpixel += ex.bg[1] * de1;
+        if (ex.ch > 2) bg_dot_dpixel += ex.bg[2] * de2;
+    }
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    const int n = (int)__reduce_max_sync(full, last_contributor);
+    if (n == 0) return;
+
+    float T = T_final;
+    float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;      // accum_rec (advanced form, see below)
+    float ae0 = 0.f, ae1 = 0.f, ae2 = 0.f;      // same for the extra channels
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    auto load_extra = [&](uint32_t id) {
+        const float* f = ex.feat + (size_t)id * ex.ch;
+        x0 = __ldg(f);
+        x1 = ex.ch > 1 ? __ldg(f + 1) : 0.f;
+        x2 = ex.ch > 2 ? __ldg(f + 2) : 0.f;
+    };
+
+    uint32_t id_cur = 0, id_next = 0;
+    float4 r0, r1, r2;
+    r0 = r1 = r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < n) {
+        id_cur = point_list[range.x + (n - 1 - lane)];
+        const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
+        r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+        if (kExtra) load_extra(id_cur);
+    }
+    if (32 + lane < n) id_next = point_list[range.x + (n - 1 - 32 - lane)];
+
+    for (int base = 0; base < n; base += 32) {
+        const bool hit = (base + lane < n) && overlaps(lox, hix, r0.x, r2.y) && overlaps(loy, hiy, r0.y, r2.z);
+        const uint32_t bits = __ballot_sync(full, hit);
+        const int nhit = __popc(bits);
+        if (hit) {
+            const int slot = __popc(bits & lt_mask);
+            slab.x[slot] = r0.x; slab.y[slot] = r0.y; slab.A[slot] = r0.z; slab.B[slot] = r0.w;
+            slab.C[slot] = r1.x; slab.op[slot] = r1.y; slab.r[slot] = r1.z; slab.g[slot] = r1.w; slab.b[slot] = r2.x;
+            slab.id[slot] = id_cur;
+            slab.pos[slot] = (uint32_t)(n - 1 - base - lane);
+            if (kExtra) { slabx.e0[slot] = x0; slabx.e1[slot] = x1; slabx.e2[slot] = x2; }
+        }
+        if ((nhit & 1) && lane == 0) {
+            // odd count: pad with a record that can never contribute (opacity 0, position beyond every pixel's last)
+            slab.x[nhit] = 0.f; slab.y[nhit] = 0.f; slab.A[nhit] = 0.f; slab.B[nhit] = 0.f; slab.C[nhit] = 0.f;
+            slab.op[nhit] = 0.f; slab.r[nhit] = 0.f; slab.g[nhit] = 0.f; slab.b[nhit] = 0.f;
+            slab.id[nhit] = 0u; slab.pos[nhit] = 0xffffffffu;
+            if (kExtra) { slabx.e0[nhit] = 0.f; slabx.e1[nhit] = 0.f; slabx.e2[nhit] = 0.f; }
+        }
+        id_cur = id_next;
+        if (base + 32 + lane < n) {
+            const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
+            r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+            if (kExtra) load_extra(id_cur);
+        }
+        if (base + 64 + lane < n) id_next = point_list[range.x + (n - 1 - base - 64 - lane)];
+        __syncwarp();
+
+        for (int k = 0; k < nhit; k += 2) {
+            const P2 X = ldp(slab.x, k), Y = ldp(slab.y, k), A = ldp(slab.A, k), B = ldp(slab.B, k), Cc = ldp(slab.C, k);
+            const P2 OP = ldp(slab.op, k);
+            const uint2 POS = *reinterpret_cast<const uint2*>(slab.pos + k);
+            // power = -0.5*(A dx^2 + C dy^2) - B dx dy in the reference's op order (same as the forward kernel)
+            const P2 dx = add2(X, bc(-pxf)), dy = add2(Y, bc(-pyf));
+            const P2 q = fma2(dx, mul2(dx, A), mul2(dy, mul2(dy, Cc)));
+            const P2 u = mul2(dy, mul2(dx, B));
+            const P2 power = fma2(q, bc(-0.5f), neg2(u));
+            const P2 G = exp_pair(power);
+            const P2 og = mul2(OP, G);
+            const float al0 = fminf(0.99f, og.x), al1 = fminf(0.99f, og.y);
+            const bool act0 = (POS.x < last_contributor) && !(power.x > 0.0f) && !(al0 < 1.0f / 255.0f);
+            const bool act1 = (POS.y < last_contributor) && !(power.y > 0.0f) && !(al1 < 1.0f / 255.0f);
+            if (!__any_sync(full, act0 || act1)) continue;
+
+            const P2 Rc = ldp(slab.r, k), Gc = ldp(slab.g, k), Bc = ldp(slab.b, k);
+            // 1/(1 - alpha) for both: alpha <= 0.99 keeps the argument in [0.01, 1], so MUFU.RCP + one packed Newton
+            // step (|error| < 1 ulp) needs none of __frcp_rn's range checks
+            const P2 om = add2(bc(1.0f), neg2(p2(al0, al1)));                  // 1 - alpha
+            P2 INV;
+            {
+                float i0, i1;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(om.x));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(om.y));
+                const P2 r = p2(i0, i1);
+                INV = fma2(r, fma2(neg2(om), r, bc(1.0f)), r);
+            }
+            // ---- the recurrences chain through the two Gaussians: scalar, first 2k then 2k+1 ----
+            // accum_rec is kept in its "already advanced" form: the reference advances it with the PREVIOUS
+            // contributor's (alpha, colour) just before use (backward.cu:509-512); advancing it with the CURRENT
+            // one right after use is the same arithmetic one step earlier and needs no last_alpha / last_color
+            P2 AR0, AR1, AR2, TP, AE0, AE1, AE2;
+            AR0.x = ar0; AR1.x = ar1; AR2.x = ar2;
+            if (kExtra) { AE0.x = ae0; AE1.x = ae1; AE2.x = ae2; }
+            if (act0) {
+                T = T * INV.x;
+                ar0 = al0 * Rc.x + om.x * ar0;
+                ar1 = al0 * Gc.x + om.x * ar1;
+                ar2 = al0 * Bc.x + om.x * ar2;
+                if (kExtra) {
+                    ae0 = al0 * slabx.e0[k] + om.x * ae0;
+                    ae1 = al0 * slabx.e1[k] + om.x * ae1;
+                    ae2 = al0 * slabx.e2[k] + om.x * ae2;
+                }
+            }
+            TP.x = T;
+            AR0.y = ar0; AR1.y = ar1; AR2.y = ar2;
+            if (kExtra) { AE0.y = ae0; AE1.y = ae1; AE2.y = ae2; }
+            if (act1) {
+                T = T * INV.y;
+                ar0 = al1 * Rc.y + om.y * ar0;
+                ar1 = al1 * Gc.y + om.y * ar1;
+                ar2 = al1 * Bc.y + om.y * ar2;
+                if (kExtra) {
+                    ae0 = al1 * slabx.e0[k + 1] + om.y * ae0;
+                    ae1 = al1 * slabx.e1[k + 1] + om.y * ae1;
+                    ae2 = al1 * slabx.e2[k + 1] + om.y * ae2;
+                }
+            }
+            TP.y = T;
+
+            // ---- gradient algebra on the pair; a non-contributing (lane, Gaussian) is zeroed through alpha and G ----
+            const P2 al = p2(act0 ? al0 : 0.f, act1 ? al1 : 0.f);
+            const P2 Gm = p2(act0 ? G.x : 0.f, act1 ? G.y : 0.f);
+            const P2 dch = mul2(al, TP);                                       // d(channel)/d(colour)
+            P2 dLa = fma2(add2(Rc, neg2(AR0)), bc(dp0),
+                          fma2(add2(Gc, neg2(AR1)), bc(dp1), mul2(add2(Bc, neg2(AR2)), bc(dp2))));
+            P2 V9, V10, V11;
+            if (kExtra) {
+                const P2 F0 = ldp(slabx.e0, k), F1 = ldp(slabx.e1, k), F2 = ldp(slabx.e2, k);
+                dLa = fma2(add2(F0, neg2(AE0)), bc(de0), dLa);
+                dLa = fma2(add2(F1, neg2(AE1)), bc(de1), dLa);
+                dLa = fma2(add2(F2, neg2(AE2)), bc(de2), dLa);
+                V9 = mul2(dch, bc(de0)); V10 = mul2(dch, bc(de1)); V11 = mul2(dch, bc(de2));
+            }
+            dLa = mul2(dLa, TP);
+            dLa = fma2(mul2(bc(-T_final), INV), bc(bg_dot_dpixel), dLa);
+            const P2 dL_dG = mul2(OP, dLa);
+            const P2 gdx = mul2(Gm, dx), gdy = mul2(Gm, dy);
+            const P2 dG_ddelx = fma2(neg2(gdx), A, neg2(mul2(gdy, B)));
+            const P2 dG_ddely = fma2(neg2(gdy), Cc, neg2(mul2(gdx, B)));
+            const P2 hh = mul2(dL_dG, bc(-0.5f));
+            const P2 hx = mul2(hh, gdx), hy = mul2(hh, gdy);
+            P2 V[8];
+            V[0] = mul2(mul2(dL_dG, dG_ddelx), bc(ddelx_dx));     // dL/dmean2D.x
+            V[1] = mul2(mul2(dL_dG, dG_ddely), bc(ddely_dy));     // dL/dmean2D.y
+            V[2] = mul2(hx, dx);                                  // dL/dconic.x
+            V[3] = mul2(hx, dy);                                  // dL/dconic.y
+            V[4] = mul2(hy, dy);                                  // dL/dconic.w
+            V[5] = mul2(Gm, dLa);                                 // dL/dopacity
+            V[6] = mul2(dch, bc(dp0));                            // dL/dcolour
+            V[7] = mul2(dch, bc(dp1));
+            const P2 V8 = mul2(dch, bc(dp2));
+
+            // ---- one butterfly for both Gaussians ----
+            // bit 4: lanes 0-15 keep Gaussian 2k (.x), lanes 16-31 keep Gaussian 2k+1 (.y)
+            float w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float send = lb4 ? V[i].x : V[i].y;
+                const float keep = lb4 ? V[i].y : V[i].x;
+                w[i] = keep + __shfl_xor_sync(full, send, 16);
+            }
+            float xx[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float send = lb3 ? w[i] : w[i + 4];
+                const float keep = lb3 ? w[i + 4] : w[i];
+                xx[i] = keep + __shfl_xor_sync(full, send, 8);
+            }
+            float yy[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = lb2 ? xx[i] : xx[i + 2];
+                const float keep = lb2 ? xx[i + 2] : xx[i];
+                yy[i] = keep + __shfl_xor_sync(full, send, 4);
+            }
+            float z;
+            {
+                const float send = lb1 ? yy[0] : yy[1];
+                const float keep = lb1 ? yy[1] : yy[0];
+                z = keep + __shfl_xor_sync(full, send, 2);       // value 4*b3 + 2*b2 + b1 of Gaussian b4
+            }
+            // ride-along values
+            float h;
+            if (kExtra) {
+                const P2 L[4] = {V8, V9, V10, V11};
+                float f[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float send = lb4 ? L[i].x : L[i].y;
+                    const float keep = lb4 ? L[i].y : L[i].x;
+                    f[i] = keep + __shfl_xor_sync(full, send, 16);
+                }
+                float gq[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float send = lb3 ? f[i] : f[i + 2];
+                    const float keep = lb3 ? f[i + 2] : f[i];
+                    gq[i] = keep + __shfl_xor_sync(full, send, 8);
+                }
+                {
+                    const float send = lb2 ? gq[0] : gq[1];
+                    const float keep = lb2 ? gq[1] : gq[0];
+                    h = keep + __shfl_xor_sync(full, send, 4);   // ride-along 2*b3 + b2 of Gaussian b4
+                }
+                h += __shfl_xor_sync(full, h, 2);
+            } else {
+                const float send = lb4 ? V8.x : V8.y;
+                const float keep = lb4 ? V8.y : V8.x;
+                h = keep + __shfl_xor_sync(full, send, 16);
+                h += __shfl_xor_sync(full, h, 8);
+                h += __shfl_xor_sync(full, h, 4);
+                h += __shfl_xor_sync(full, h, 2);
+            }
+            float red;
+            {
+                const float send = lb0 ? z : h;
+                const float keep = lb0 ? h : z;
+                red = keep + __shfl_xor_sync(full, send, 1);
+            }
+            if (red_lane && !(lb4 && k + 1 >= nhit)) {
+                const uint32_t gid = slab.id[k + (lb4 ? 1 : 0)];
+                atomicAdd(acc + (size_t)gid * 12 + red_slot, red);
+            }
+        }
+        __syncwarp();   // slab is rewritten by the next step
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_render_bwd_clear(const BwdArgs& a, cudaStream_t s) {
@@ -315,6 +620,18 @@ cudaError_t launch_render_bwd_clear(const BwdArgs& a, cudaStream_t s) {
 cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
     count_launch();
+    static const bool legacy = getenv("FB200_BWD_V2") != nullptr;   // A/B switch while v3 is being validated
+    if (!legacy) {
+        if (a.ex.ch > 0)
+            render_bwd_pair_kernel<true><<<T, 256, 0, s>>>(a.ranges, a.point_list, a.rec, a.prm.image_width,
+                                                           a.prm.image_height, a.tiles_x, a.in.d_background, a.final_T,
+                                                           a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+        else
+            render_bwd_pair_kernel<false><<<T, 256, 0, s>>>(a.ranges, a.point_list, a.rec, a.prm.image_width,
+                                                            a.prm.image_height, a.tiles_x, a.in.d_background, a.final_T,
+                                                            a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+        return cudaGetLastError();
+    }
     if (a.ex.ch > 0)
         render_bwd_kernel<true><<<T, 256, 0, s>>>(a.ranges, a.point_list, a.rec, a.prm.image_width,
                                                   a.prm.image_height, a.tiles_x, a.in.d_background, a.final_T,

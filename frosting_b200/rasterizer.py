@@ -201,14 +201,19 @@ def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None):
         if g.dtype != torch.float32:
             g = g.float()
         g = g.contiguous()
-        # one allocation carved into the eight gradient tensors (each offset is a multiple of 4 floats)
-        n = [3 * P, 3 * P, 3 * P, P, 6 * P, 3 * M * P, 3 * P, 4 * P]
+        # one allocation carved into the gradient tensors the caller can use (each offset a multiple of 4 floats);
+        # dL/dcolors on the SH path, dL/dcov3D on the scale/rotation path and dL/dscales, dL/drotations on the
+        # precomputed-covariance path are never returned (`backward` below) and are not materialised
+        has_sh, has_col = call.inp.d_shs is not None, call.inp.d_colors_precomp is not None
+        has_cov = call.inp.d_cov3D_precomp is not None
+        n = [3 * P, 3 * P, 3 * P if has_col else 0, P, 6 * P if has_cov else 0, 3 * M * P if has_sh else 0,
+             0 if has_cov else 3 * P, 0 if has_cov else 4 * P]
         offs, tot = [], 0
         for c in n:
             offs.append(tot)
             tot += (c + 3) // 4 * 4
         gslab = torch.empty((max(tot, 1),), dtype=torch.float32, device=device)
-        cut = lambda k, shape: gslab[offs[k]:offs[k] + n[k]].view(shape)
+        cut = lambda k, shape: gslab[offs[k]:offs[k] + n[k]].view(shape) if n[k] or P == 0 else None
         dL_dmeans3D, dL_dmeans2D, dL_dcolors = cut(0, (P, 3)), cut(1, (P, 3)), cut(2, (P, 3))
         dL_dopacity, dL_dcov3D, dL_dsh = cut(3, (P, 1)), cut(4, (P, 6)), cut(5, (P, M, 3))
         dL_dscales, dL_drotations = cut(6, (P, 3)), cut(7, (P, 4))

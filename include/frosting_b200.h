@@ -139,12 +139,12 @@ int fb200_forward_raster(const fb200_params* prm, const fb200_inputs* in, const 
  * All are fully written by the call (invisible Gaussians get zeros); no pre-zeroing needed. */
 typedef struct fb200_grads {
     float* d_dL_dmeans2D;     /* [P,3] (z = 0) */
-    float* d_dL_dcolors;      /* [P,3] */
+    float* d_dL_dcolors;      /* [P,3]; may be NULL when colours come from SH (then an intermediate, not written) */
     float* d_dL_dopacity;     /* [P,1] */
     float* d_dL_dmeans3D;     /* [P,3] */
-    float* d_dL_dcov3D;       /* [P,6] */
+    float* d_dL_dcov3D;       /* [P,6]; may be NULL unless d_cov3D_precomp is given */
     float* d_dL_dsh;          /* [P,M,3] (may be NULL when M == 0) */
-    float* d_dL_dscales;      /* [P,3] */
+    float* d_dL_dscales;      /* [P,3]; these two may be NULL when d_cov3D_precomp is given */
     float* d_dL_drotations;   /* [P,4] */
 } fb200_grads;
 
