@@ -56,6 +56,7 @@ class Workspace(C.Structure):
         ("d_binning", C.c_void_p), ("binning_bytes", C.c_size_t),
         ("binning_capacity", C.c_int64),
         ("d_status", C.c_void_p),
+        ("acc_zeroed_by_forward", C.c_int32),
     ]
 
 

@@ -223,6 +223,13 @@ int fb200_forward_geometry(const fb200_params* prm, const fb200_inputs* in, cons
     { StageTimer t(FB200_STAGE_PREPROCESS, s);
       if ((rc = stage(launch_preprocess_fwd(a, s), "preprocess", debug, s)) != FB200_OK) return rc;
       if ((rc = stage(launch_tile_scan(a, s), "tile scan", debug, s)) != FB200_OK) return rc; }
+    if (ws->acc_zeroed_by_forward && prm->P > 0) {
+        // backward's accumulators: cleared here, in the shadow of the host's wait for the instance count
+        const GeomLayout gl((size_t)prm->P);
+        float* acc = reinterpret_cast<float*>(align128(ws->d_geom) + gl.acc);
+        if ((rc = stage(cudaMemsetAsync(acc, 0, sizeof(float) * 12 * (size_t)prm->P, s), "accumulator clear", debug, s)) != FB200_OK)
+            return rc;
+    }
     return FB200_OK;
 }
 
@@ -291,7 +298,8 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     a.g = *grads;
     if ((rc = setup_extra(prm, false, true, a.ex)) != FB200_OK) return rc;
 
-    if ((rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
+    if (!ws->acc_zeroed_by_forward &&
+        (rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
     { StageTimer t(FB200_STAGE_RENDER_BWD, s);
       if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc; }
     { StageTimer t(FB200_STAGE_GEOM_BWD, s);

@@ -231,6 +231,12 @@ preprocess_fwd_kernel(FwdArgs a) {
         __trap();
     }
     if (a.in.d_visibility != nullptr && a.in.d_visibility[idx] == 0) keep = false;
+    if (keep && a.in.d_shs != nullptr) {
+        // the SH row (192 B at degree 3) is consumed last, after a chain of dependent loads; start it moving now
+        const char* row = reinterpret_cast<const char*>(a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+        if (a.prm.sh_coeffs * 12 > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));
+    }
 
     int radius = 0;
     uint2 rect = make_uint2(0u, 0u);

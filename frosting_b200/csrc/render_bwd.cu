@@ -327,21 +327,23 @@ struct __align__(16) PairSlabX {
 
 __device__ __forceinline__ P2 ldp(const float* a, int k) { return *reinterpret_cast<const float2*>(a + k); }
 
-template <bool kExtra>
-__global__ void __launch_bounds__(256, kExtra ? 2 : 3)
+template <bool kExtra, int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, (kExtra ? 16 : 24) / kWarps)
 render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
                        float* __restrict__ acc, const int32_t* __restrict__ status, const ExtraArgs ex) {
-    __shared__ PairSlab slabs[kWarpsPerTile];
-    __shared__ PairSlabX slabs_x[kExtra ? kWarpsPerTile : 1];
+    __shared__ PairSlab slabs[kWarps];
+    __shared__ PairSlabX slabs_x[kExtra ? kWarps : 1];
     if (status[FB200_ST_OVERFLOW]) return;
 
     const unsigned full = 0xffffffffu;
-    const int tile = blockIdx.x;
+    constexpr int kSplit = kWarpsPerTile / kWarps;
+    const int tile = blockIdx.x / kSplit;
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    const int warp = threadIdx.x >> 5;
+    const int wslot = threadIdx.x >> 5;
+    const int warp = (blockIdx.x % kSplit) * kWarps + wslot;      // sub-tile index inside the tile
     int lane;
     unsigned lt_mask;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
@@ -351,8 +353,8 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     // values: slot 8 (kExtra: 8 + ((lane >> 2) & 3)) of Gaussian (lane >> 4)
     const bool red_lane = !lb0 || (kExtra ? (lane & 3) == 1 : (lane & 15) == 1);
     const int red_slot = lb0 ? (kExtra ? 8 + ((lane >> 2) & 3) : 8) : ((lane >> 1) & 7);
-    PairSlab& slab = slabs[warp];
-    PairSlabX& slabx = slabs_x[kExtra ? warp : 0];
+    PairSlab& slab = slabs[wslot];
+    PairSlabX& slabx = slabs_x[kExtra ? wslot : 0];
     const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
     const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
     const int pix_x = sub_x0 + (lane & 7), pix_y = sub_y0 + (lane >> 3);
@@ -539,24 +541,26 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             // bit 4: lanes 0-15 keep Gaussian 2k (.x), lanes 16-31 keep Gaussian 2k+1 (.y)
             float w[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float send = lb4 ? V[i].x : V[i].y;
-                const float keep = lb4 ? V[i].y : V[i].x;
-                w[i] = keep + __shfl_xor_sync(full, send, 16);
+            for (int i = 0; i < 8; i += 2) {
+                const P2 send = p2(lb4 ? V[i].x : V[i].y, lb4 ? V[i + 1].x : V[i + 1].y);
+                const P2 keep = p2(lb4 ? V[i].y : V[i].x, lb4 ? V[i + 1].y : V[i + 1].x);
+                const P2 sum = add2(keep, p2(__shfl_xor_sync(full, send.x, 16), __shfl_xor_sync(full, send.y, 16)));
+                w[i] = sum.x; w[i + 1] = sum.y;
             }
             float xx[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float send = lb3 ? w[i] : w[i + 4];
-                const float keep = lb3 ? w[i + 4] : w[i];
-                xx[i] = keep + __shfl_xor_sync(full, send, 8);
+            for (int i = 0; i < 4; i += 2) {
+                const P2 send = p2(lb3 ? w[i] : w[i + 4], lb3 ? w[i + 1] : w[i + 5]);
+                const P2 keep = p2(lb3 ? w[i + 4] : w[i], lb3 ? w[i + 5] : w[i + 1]);
+                const P2 sum = add2(keep, p2(__shfl_xor_sync(full, send.x, 8), __shfl_xor_sync(full, send.y, 8)));
+                xx[i] = sum.x; xx[i + 1] = sum.y;
             }
             float yy[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float send = lb2 ? xx[i] : xx[i + 2];
-                const float keep = lb2 ? xx[i + 2] : xx[i];
-                yy[i] = keep + __shfl_xor_sync(full, send, 4);
+            {
+                const P2 send = p2(lb2 ? xx[0] : xx[2], lb2 ? xx[1] : xx[3]);
+                const P2 keep = p2(lb2 ? xx[2] : xx[0], lb2 ? xx[3] : xx[1]);
+                const P2 sum = add2(keep, p2(__shfl_xor_sync(full, send.x, 4), __shfl_xor_sync(full, send.y, 4)));
+                yy[0] = sum.x; yy[1] = sum.y;
             }
             float z;
             {
@@ -621,15 +625,18 @@ cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
     count_launch();
     static const bool legacy = getenv("FB200_BWD_V2") != nullptr;   // A/B switch while v3 is being validated
+    static const int warps = getenv("FB200_BWD_WARPS") ? atoi(getenv("FB200_BWD_WARPS")) : 4;   // measured: 4-warp CTAs (half tiles) beat 8 and 2
     if (!legacy) {
-        if (a.ex.ch > 0)
-            render_bwd_pair_kernel<true><<<T, 256, 0, s>>>(a.ranges, a.point_list, a.rec, a.prm.image_width,
-                                                           a.prm.image_height, a.tiles_x, a.in.d_background, a.final_T,
-                                                           a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
-        else
-            render_bwd_pair_kernel<false><<<T, 256, 0, s>>>(a.ranges, a.point_list, a.rec, a.prm.image_width,
-                                                            a.prm.image_height, a.tiles_x, a.in.d_background, a.final_T,
-                                                            a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+#define FB200_LAUNCH_BWD(EX, KW)                                                                                   \
+    render_bwd_pair_kernel<EX, KW><<<T * (kWarpsPerTile / KW), 32 * KW, 0, s>>>(                                    \
+        a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,        \
+        a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex)
+        if (a.ex.ch > 0) {
+            if (warps == 2) FB200_LAUNCH_BWD(true, 2); else if (warps == 8) FB200_LAUNCH_BWD(true, 8); else FB200_LAUNCH_BWD(true, 4);
+        } else {
+            if (warps == 2) FB200_LAUNCH_BWD(false, 2); else if (warps == 8) FB200_LAUNCH_BWD(false, 8); else FB200_LAUNCH_BWD(false, 4);
+        }
+#undef FB200_LAUNCH_BWD
         return cudaGetLastError();
     }
     if (a.ex.ch > 0)

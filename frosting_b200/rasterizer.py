@@ -59,6 +59,9 @@ def _sizes(L, P, W, H):
     return v
 
 
+_capacity_hint = {}     # (device, P, W, H) -> binning capacity to pre-allocate
+
+
 def _pinned_status(device):
     # one pinned 32-byte mailbox per device: cudaHostAlloc per call would cost more than the frame
     t = _pinned.get(device.index)
@@ -166,15 +169,24 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
         # the caller's loss/backward launches queue up behind it while the GPU is busy.
         ws = Workspace(d_geom=geom.data_ptr(), geom_bytes=geom.numel(),
                        d_image=image.data_ptr(), image_bytes=image.numel(),
-                       d_binning=None, binning_bytes=0, binning_capacity=0, d_status=status.data_ptr())
+                       d_binning=None, binning_bytes=0, binning_capacity=0, d_status=status.data_ptr(),
+                       # a backward will follow: clear its accumulators while the host waits for R (below)
+                       acc_zeroed_by_forward=1 if torch.is_grad_enabled() else 0)
         rptr = C.c_void_p(radii.data_ptr()) if P > 0 else None
         sptr = C.c_void_p(stream.cuda_stream)
         _lib.check(L.fb200_forward_geometry(C.byref(prm), C.byref(inp), C.byref(ws), rptr, sptr))
         status_host.copy_(status, non_blocking=True)
+        # the binning buffer is allocated BEFORE the wait from the last count seen for this problem size, so that the
+        # host's critical path after the wait is one comparison and one library call
+        hint_key = (device.index, P, W, H)
+        capacity = _capacity_hint.get(hint_key, 0)
+        binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device) if capacity else None
         stream.synchronize()
         num_rendered = int(status_host[_lib.ST_NUM_RENDERED])
-        capacity = max(num_rendered, 1)
-        binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
+        if num_rendered > capacity or binning is None:
+            capacity = max(num_rendered, 1)
+            binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
+        _capacity_hint[hint_key] = max(int(num_rendered * 1.05) + 1024, 1)
         ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
         _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
                                           C.c_void_p(out_color.data_ptr()), rptr, sptr))
@@ -234,6 +246,7 @@ def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None):
                                     C.c_void_p(radii.data_ptr()) if P > 0 else None,
                                     C.c_void_p(g.data_ptr()), C.byref(grads),
                                     C.c_void_p(stream.cuda_stream)))
+        call.ws.acc_zeroed_by_forward = 0      # a second backward over this forward must clear them itself
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dextra
 
 

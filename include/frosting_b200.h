@@ -103,6 +103,12 @@ typedef struct fb200_workspace {
     void* d_binning; size_t binning_bytes; /* per-instance state, kept for backward */
     int64_t binning_capacity;              /* instances the binning buffer was sized for */
     int32_t* d_status;                     /* [FB200_STATUS_WORDS] device words, see below */
+    int32_t acc_zeroed_by_forward;         /* backward's per-Gaussian accumulators (48 B each, inside d_geom) must be zero
+                                              when fb200_backward starts.  0: fb200_backward clears them itself.
+                                              1: fb200_forward_geometry clears them (stream-ordered, while the host
+                                              waits for the instance count) and fb200_backward skips its clear; the
+                                              caller resets the field to 0 before any further backward over the same
+                                              forward state */
 } fb200_workspace;
 
 /* d_status words written by fb200_forward (stream-ordered; copy back after the call). */

@@ -332,3 +332,24 @@ def test_fused_frosting_attributes_match_torch_chain(cuda_device):
     # for a handful of pixel/Gaussian pairs (each worth up to ~4e-3): compare statistically
     d = (c1 - c2).abs()
     assert (d > 1e-4).float().mean().item() < 1e-3 and d.max().item() < 2e-2
+
+
+def test_backward_twice_over_one_forward(cuda_device):
+    """The accumulators are cleared by the forward for the FIRST backward only (fb200_workspace.acc_zeroed_by_forward);
+    a second backward over the same graph must clear them itself and give the same gradients."""
+    P, W, H = 20_000, 256, 160
+    cam, g, rs = scene(P, W, H, 9, 2, cuda_device, 0.0)
+    leaves = {k: g[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    m2 = torch.zeros(P, 3, device=cuda_device, requires_grad=True)
+    color, _ = fb.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                         shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+    cot = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    loss = (color * cot).sum()
+    loss.backward(retain_graph=True)
+    first = {k: v.grad.clone() for k, v in leaves.items()}
+    for v in leaves.values():
+        v.grad = None
+    loss.backward()
+    for k, v in leaves.items():
+        m, frac = rel_err_stats(v.grad, first[k])
+        assert m <= 1e-4, (k, m)          # equal up to the order of the float atomics
