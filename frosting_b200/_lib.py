@@ -57,6 +57,7 @@ class Workspace(C.Structure):
         ("binning_capacity", C.c_int64),
         ("d_status", C.c_void_p),
         ("acc_zeroed_by_forward", C.c_int32),
+        ("h_status", C.c_void_p),
     ]
 
 

@@ -199,6 +199,7 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     a.ranges = reinterpret_cast<uint2*>(im + il.ranges);
     a.tile_count = reinterpret_cast<uint32_t*>(im + il.tile_count);
     a.cursor = reinterpret_cast<uint32_t*>(im + il.cursor);
+    a.list_tiny = reinterpret_cast<uint32_t*>(im + il.list_tiny);
     a.list_small = reinterpret_cast<uint32_t*>(im + il.list_small);
     a.list_large = reinterpret_cast<uint32_t*>(im + il.list_large);
     a.list_huge = reinterpret_cast<uint32_t*>(im + il.list_huge);
@@ -242,7 +243,7 @@ int fb200_forward_raster(const fb200_params* prm, const fb200_inputs* in, const 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool debug = (prm->debug & 1) != 0;
     { StageTimer t(FB200_STAGE_BINNING, s);
-      if ((rc = stage(launch_binning(a, s), "binning", debug, s)) != FB200_OK) return rc; }
+      if ((rc = stage(launch_binning(a, s, ws->h_status), "binning", debug, s)) != FB200_OK) return rc; }
     { StageTimer t(FB200_STAGE_RENDER_FWD, s);
       if ((rc = stage(launch_render_fwd(a, s), "render", debug, s)) != FB200_OK) return rc; }
     return FB200_OK;
@@ -252,7 +253,10 @@ int fb200_forward(const fb200_params* prm, const fb200_inputs* in, const fb200_w
                   float* d_out_color, int32_t* d_radii, void* stream) {
     int rc = fb200_forward_geometry(prm, in, ws, d_radii, stream);
     if (rc != FB200_OK) return rc;
-    return fb200_forward_raster(prm, in, ws, d_out_color, d_radii, stream);
+    if (!ws) return fail(FB200_EINVAL, "null argument struct%s");
+    fb200_workspace one_phase = *ws;
+    one_phase.h_status = nullptr;      // nobody has synchronised: the host cannot know this frame's status words
+    return fb200_forward_raster(prm, in, &one_phase, d_out_color, d_radii, stream);
 }
 
 int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,

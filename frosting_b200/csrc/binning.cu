@@ -23,22 +23,32 @@ namespace {
 typedef unsigned long long u64;
 
 // ---- tile scan: counts -> ranges, cursors, sort work lists, status ---------------------------------
+// One CTA (the host is waiting for the instance count this kernel produces, so it is latency that matters):
+// the counts are staged in shared memory with coalesced loads, each thread then owns a contiguous run of tiles.
+constexpr int kScanStage = 10240;   // tiles staged in shared memory (40 KB); larger grids read global memory twice
+
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ list_small,
+                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ list_tiny, uint32_t* __restrict__ list_small,
                  uint32_t* __restrict__ list_large, uint32_t* __restrict__ list_huge,
                  uint32_t* __restrict__ counters, long long capacity, int32_t* __restrict__ status) {
+    __shared__ uint32_t staged[kScanStage];
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t s_n[3];
+    __shared__ uint32_t s_n[4];
     __shared__ uint32_t s_max;
     const int tid = threadIdx.x;
-    if (tid < 3) s_n[tid] = 0;
+    if (tid < 4) s_n[tid] = 0;
     if (tid == 0) s_max = 0;
+    const bool use_stage = T <= kScanStage;
+    if (use_stage)
+        for (int t = tid; t < T; t += 1024) staged[t] = tile_count[t];
+    __syncthreads();
+    const uint32_t* cnt = use_stage ? staged : tile_count;
     const int per = (T + 1023) / 1024;
     const int begin = min(T, tid * per), end = min(T, begin + per);
     uint32_t local = 0, lmax = 0;
     for (int t = begin; t < end; ++t) {
-        uint32_t c = tile_count[t];
+        uint32_t c = cnt[t];
         local += c;
         lmax = max(lmax, c);
     }
@@ -64,12 +74,13 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     __syncthreads();
     uint32_t run = warp_sums[tid >> 5] + incl - local;
     for (int t = begin; t < end; ++t) {
-        uint32_t c = tile_count[t];
+        uint32_t c = cnt[t];
         // untouched tiles keep (0,0) exactly like the reference's memset + identifyTileRanges
         ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
         cursor[t] = run;
-        if (c > 1) {
-            if (c <= (uint32_t)kSortSmallMax) list_small[atomicAdd(&s_n[0], 1u)] = t;
+        if (c >= 1) {
+            if (c <= (uint32_t)kSortTinyMax) list_tiny[atomicAdd(&s_n[3], 1u)] = t;
+            else if (c <= (uint32_t)kSortSmallMax) list_small[atomicAdd(&s_n[0], 1u)] = t;
             else if (c <= (uint32_t)kSortMediumMax) list_large[atomicAdd(&s_n[1], 1u)] = t;
             else list_huge[atomicAdd(&s_n[2], 1u)] = t;
         }
@@ -83,6 +94,7 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
         status[FB200_ST_MAX_TILE] = (int32_t)s_max;
     }
     if (tid < 3) counters[tid] = s_n[tid];
+    if (tid == 3) counters[4] = s_n[3];
 }
 
 // ---- scatter: one (depth_bits<<32 | idx) key per (Gaussian, tile) into the tile's segment ----------
@@ -299,6 +311,118 @@ tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __res
     }
 }
 
+// ---- tiny lists: one WARP per tile ---------------------------------------------------------------------
+// Most tiles of a real frame hold a few hundred instances (C3: 428 on average).  Spreading such a list over the 8
+// warps of a CTA leaves each warp one or two 32-key steps per pass between seven CTA barriers -- the kernel was
+// barrier/latency bound (profiles/r01_c3_v2_summary.json: issue-active 39 %, barrier the top stall).  Here a warp
+// sorts a whole tile by itself (same stable LSD radix, same ballot ranking, __syncwarp only), so an SM runs dozens of
+// independent tile sorts and the work is throughput-bound.
+template <int kWarps>
+__global__ void __launch_bounds__(32 * kWarps)
+tile_sort_warp_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
+                      const uint2* __restrict__ ranges, u64* __restrict__ keys, uint32_t* __restrict__ point_list,
+                      const int32_t* __restrict__ status) {
+    __shared__ u64 s_a[kWarps][kSortTinyMax];
+    __shared__ u64 s_b[kWarps][kSortTinyMax];
+    __shared__ uint32_t s_cnt[kWarps][256];
+    if (status[FB200_ST_OVERFLOW]) return;
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t count = *n_list;
+    uint32_t* cnt = s_cnt[warp];
+    for (uint32_t w = blockIdx.x * kWarps + warp; w < count; w += gridDim.x * kWarps) {
+        const uint2 rg = ranges[list[w]];
+        const int n = (int)(rg.y - rg.x);
+        u64* g = keys + rg.x;
+        if (n == 1) {                                   // nothing to sort, only the point_list entry
+            if (lane == 0) point_list[rg.x] = (uint32_t)g[0];
+            continue;
+        }
+        u64* src = s_a[warp];
+        u64* dst = s_b[warp];
+        for (int i = lane; i < n; i += 32) src[i] = g[i];
+        __syncwarp();
+        for (int shift = 32; shift < 64; shift += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cnt[lane + 32 * k] = 0;
+            __syncwarp();
+            // 1. digit histogram
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const bool have = i < n;
+                const uint32_t d = have ? (uint32_t)(src[i] >> shift) & 0xffu : 0u;
+                const unsigned peers = digit_peers(d, have);
+                if (have && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+                __syncwarp();
+            }
+            // 2. exclusive offsets: lane l owns digits 8l .. 8l+7; a digit shared by every key makes the pass an identity
+            uint32_t c[8];
+            uint32_t tot = 0;
+            bool uniform = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                c[k] = cnt[8 * lane + k];
+                uniform |= c[k] == (uint32_t)n;
+                tot += c[k];
+            }
+            if (__any_sync(full, uniform)) continue;
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(full, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t base = incl - tot;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                cnt[8 * lane + k] = base;
+                base += c[k];
+            }
+            __syncwarp();
+            // 3. stable scatter, 32 keys at a time in list order
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const bool have = i < n;
+                const u64 k = have ? src[i] : 0ull;
+                const uint32_t d = have ? (uint32_t)(k >> shift) & 0xffu : 0u;
+                const unsigned peers = digit_peers(d, have);
+                uint32_t off = 0;
+                if (have) off = cnt[d] + __popc(peers & ((1u << lane) - 1u));
+                __syncwarp();
+                if (have) {
+                    dst[off] = k;
+                    if ((__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+                }
+                __syncwarp();
+            }
+            u64* t = src; src = dst; dst = t;
+        }
+        // 4. order runs of equal depth by Gaussian index (rare: exact float ties)
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t d = (uint32_t)(src[i] >> 32);
+            const bool run_start = (i == 0 || (uint32_t)(src[i - 1] >> 32) != d) && (i + 1 < n) &&
+                                   (uint32_t)(src[i + 1] >> 32) == d;
+            if (run_start) {
+                int e = i + 1;
+                while (e < n && (uint32_t)(src[e] >> 32) == d) ++e;
+                for (int x = i + 1; x < e; ++x) {          // insertion sort of the run [i, e)
+                    const u64 kx = src[x];
+                    int y = x - 1;
+                    while (y >= i && src[y] > kx) { src[y + 1] = src[y]; --y; }
+                    src[y + 1] = kx;
+                }
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const u64 k = src[i];
+            g[i] = k;
+            point_list[rg.x + i] = (uint32_t)k;
+        }
+        __syncwarp();
+    }
+}
+
 // Lists longer than the shared-memory class: same algorithm, ping-pong between the key array and a
 // scratch array in global memory (L2-resident for any realistic tile).
 template <int kThreads>
@@ -325,22 +449,11 @@ tile_sort_global_kernel(const uint32_t* __restrict__ list, const uint32_t* __res
     }
 }
 
-// tiles with exactly one instance need no sort, only the point_list entry
-__global__ void __launch_bounds__(256)
-single_instance_kernel(int T, const uint2* __restrict__ ranges, const u64* __restrict__ keys,
-                       uint32_t* __restrict__ point_list, const int32_t* __restrict__ status) {
-    if (status[FB200_ST_OVERFLOW]) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const uint2 rg = ranges[t];
-    if (rg.y - rg.x == 1u) point_list[rg.x] = (uint32_t)keys[rg.x];
-}
-
 }  // namespace
 
 cudaError_t launch_tile_scan(const FwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
-    tile_scan_kernel<<<1, 1024, 0, s>>>(T, a.tile_count, a.ranges, a.cursor, a.list_small, a.list_large,
+    tile_scan_kernel<<<1, 1024, 0, s>>>(T, a.tile_count, a.ranges, a.cursor, a.list_tiny, a.list_small, a.list_large,
                                         a.list_huge, a.counters, a.capacity, a.status);
     count_launch();
     return cudaGetLastError();
@@ -351,39 +464,54 @@ __global__ void check_capacity_kernel(long long capacity, int32_t* __restrict__ 
     status[FB200_ST_OVERFLOW] = ((long long)status[FB200_ST_NUM_RENDERED] > capacity) ? 1 : 0;
 }
 
-cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s) {
+// h_status: the status words of the geometry phase as the HOST has read them (or NULL).  With them the launches
+// that would find an empty work list are skipped (the lists live on the device, so without them every class is
+// launched for the worst case and exits at once).
+cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_status) {
     const int T = a.tiles_x * a.tiles_y;
-    check_capacity_kernel<<<1, 1, 0, s>>>(a.capacity, a.status);
-    count_launch();
+    const int max_tile = h_status ? h_status[FB200_ST_MAX_TILE] : 0x7fffffff;
+    const bool capacity_known_ok = h_status && (long long)h_status[FB200_ST_NUM_RENDERED] <= a.capacity &&
+                                   h_status[FB200_ST_OVERFLOW] == 0;
+    if (!capacity_known_ok) {
+        check_capacity_kernel<<<1, 1, 0, s>>>(a.capacity, a.status);
+        count_launch();
+    }
     if (a.prm.P > 0) {
         scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a.prm.P, a.tiles_x, a.rect, a.depth, a.cursor,
                                                              a.keys, a.status);
         count_launch();
     }
-    single_instance_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, a.ranges, a.keys, a.point_list, a.status);
-    count_launch(4);   // + the three sort kernels below
-    // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides
-    // over its list.
+    // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides over its list.
     {
+        constexpr int kWarps = 4;                        // 4 x 9 KB of shared memory per CTA
+        const int grid = min((T + kWarps - 1) / kWarps, 148 * 6);
+        tile_sort_warp_kernel<kWarps><<<grid, 32 * kWarps, 0, s>>>(a.list_tiny, a.counters + 4, a.ranges, a.keys,
+                                                                   a.point_list, a.status);
+        count_launch();
+    }
+    if (max_tile > kSortTinyMax) {
         const int grid = min(T, 148 * 5);
         tile_sort_shared_kernel<256, kSortSmallMax, false><<<grid, 256, 0, s>>>(
             a.list_small, a.counters + 0, a.ranges, a.keys, a.point_list, a.status);
+        count_launch();
     }
-    {
+    if (max_tile > kSortSmallMax) {
         // medium lists (2048 < n <= 8192): 1024 threads, ping-pong buffers + per-warp counters in 160 KB of
         // dynamic shared memory, one CTA per SM
         const int smem = 2 * 8 * kSortMediumMax + 32 * 256 * 4;
-        cudaError_t e = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortMediumMax, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
+        static const cudaError_t attr = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortMediumMax, true>,
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (attr != cudaSuccess) return attr;
         const int grid = min(T, 148);
         tile_sort_shared_kernel<1024, kSortMediumMax, true><<<grid, 1024, smem, s>>>(
             a.list_large, a.counters + 1, a.ranges, a.keys, a.point_list, a.status);
+        count_launch();
     }
-    {
+    if (max_tile > kSortMediumMax) {
         const int grid = min(T, 148 * 2);
         tile_sort_global_kernel<1024><<<grid, 1024, 0, s>>>(a.list_huge, a.counters + 2, a.ranges, a.keys,
                                                             a.keys_scratch, a.point_list, a.status);
+        count_launch();
     }
     return cudaGetLastError();
 }

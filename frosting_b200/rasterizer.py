@@ -188,6 +188,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
             binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
         _capacity_hint[hint_key] = max(int(num_rendered * 1.05) + 1024, 1)
         ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
+        ws.h_status = status_host.data_ptr()      # the mailbox holds this frame's status words until the next forward
         _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
                                           C.c_void_p(out_color.data_ptr()), rptr, sptr))
         _last["num_rendered"] = num_rendered

@@ -109,6 +109,9 @@ typedef struct fb200_workspace {
                                               waits for the instance count) and fb200_backward skips its clear; the
                                               caller resets the field to 0 before any further backward over the same
                                               forward state */
+    const int32_t* h_status;               /* optional HOST copy of the status words written by fb200_forward_geometry,
+                                              read by the caller after synchronising the stream; fb200_forward_raster
+                                              then skips launches it can tell are empty.  NULL: launch for the worst case */
 } fb200_workspace;
 
 /* d_status words written by fb200_forward (stream-ordered; copy back after the call). */
