@@ -14,6 +14,8 @@
 // (depth_bits << 32 | gaussian_index) -- a total order that equals the reference's stable order.
 // Global traffic: 8 B written + 8 B read + 4 B written per instance instead of ~150 B/instance for
 // a 6-pass global radix sort.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace fb200 {
@@ -34,10 +36,10 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
                  uint32_t* __restrict__ counters, long long capacity, int32_t* __restrict__ status) {
     __shared__ uint32_t staged[kScanStage];
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t s_n[4];
+    __shared__ u64 cls_sums[2][32];
+    __shared__ u64 cls_total[2];
     __shared__ uint32_t s_max;
     const int tid = threadIdx.x;
-    if (tid < 4) s_n[tid] = 0;
     if (tid == 0) s_max = 0;
     const bool use_stage = T <= kScanStage;
     if (use_stage)
@@ -73,16 +75,53 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     }
     __syncthreads();
     uint32_t run = warp_sums[tid >> 5] + incl - local;
+    // work-list slots come from a second block scan (per-thread counts of the four classes, two per 64-bit word)
+    // instead of shared-memory atomics: 8 k returning atomics on four addresses serialise to ~30 k cycles
+    u64 cls_a = 0, cls_b = 0;     // (tiny | small << 32), (large | huge << 32)
+    for (int t = begin; t < end; ++t) {
+        const uint32_t c = cnt[t];
+        if (c >= 1) {
+            if (c <= (uint32_t)kSortTinyMax) cls_a += 1ull;
+            else if (c <= (uint32_t)kSortSmallMax) cls_a += 1ull << 32;
+            else if (c <= (uint32_t)kSortMediumMax) cls_b += 1ull;
+            else cls_b += 1ull << 32;
+        }
+    }
+    u64 inc_a = cls_a, inc_b = cls_b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 na = __shfl_up_sync(0xffffffffu, inc_a, o), nb = __shfl_up_sync(0xffffffffu, inc_b, o);
+        if ((tid & 31) >= o) { inc_a += na; inc_b += nb; }
+    }
+    __syncthreads();                 // warp_sums is reused below
+    if ((tid & 31) == 31) { cls_sums[0][tid >> 5] = inc_a; cls_sums[1][tid >> 5] = inc_b; }
+    __syncthreads();
+    if (tid < 32) {
+        const u64 wa = cls_sums[0][tid], wb = cls_sums[1][tid];
+        u64 ia = wa, ib = wb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 na = __shfl_up_sync(0xffffffffu, ia, o), nb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (tid >= o) { ia += na; ib += nb; }
+        }
+        cls_sums[0][tid] = ia - wa;
+        cls_sums[1][tid] = ib - wb;
+        if (tid == 31) { cls_total[0] = ia; cls_total[1] = ib; }
+    }
+    __syncthreads();
+    const u64 ex_a = cls_sums[0][tid >> 5] + inc_a - cls_a, ex_b = cls_sums[1][tid >> 5] + inc_b - cls_b;
+    uint32_t at_tiny = (uint32_t)ex_a, at_small = (uint32_t)(ex_a >> 32);
+    uint32_t at_large = (uint32_t)ex_b, at_huge = (uint32_t)(ex_b >> 32);
     for (int t = begin; t < end; ++t) {
         uint32_t c = cnt[t];
         // untouched tiles keep (0,0) exactly like the reference's memset + identifyTileRanges
         ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
         cursor[t] = run;
         if (c >= 1) {
-            if (c <= (uint32_t)kSortTinyMax) list_tiny[atomicAdd(&s_n[3], 1u)] = t;
-            else if (c <= (uint32_t)kSortSmallMax) list_small[atomicAdd(&s_n[0], 1u)] = t;
-            else if (c <= (uint32_t)kSortMediumMax) list_large[atomicAdd(&s_n[1], 1u)] = t;
-            else list_huge[atomicAdd(&s_n[2], 1u)] = t;
+            if (c <= (uint32_t)kSortTinyMax) list_tiny[at_tiny++] = t;
+            else if (c <= (uint32_t)kSortSmallMax) list_small[at_small++] = t;
+            else if (c <= (uint32_t)kSortMediumMax) list_large[at_large++] = t;
+            else list_huge[at_huge++] = t;
         }
         run += c;
     }
@@ -93,8 +132,12 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
         status[FB200_ST_OVERFLOW] = ((long long)run > capacity) ? 1 : 0;
         status[FB200_ST_MAX_TILE] = (int32_t)s_max;
     }
-    if (tid < 3) counters[tid] = s_n[tid];
-    if (tid == 3) counters[4] = s_n[3];
+    if (tid == 0) {
+        counters[4] = (uint32_t)cls_total[0];            // tiny
+        counters[0] = (uint32_t)(cls_total[0] >> 32);    // small
+        counters[1] = (uint32_t)cls_total[1];            // large
+        counters[2] = (uint32_t)(cls_total[1] >> 32);    // huge
+    }
 }
 
 // ---- scatter: one (depth_bits<<32 | idx) key per (Gaussian, tile) into the tile's segment ----------
@@ -464,6 +507,30 @@ __global__ void check_capacity_kernel(long long capacity, int32_t* __restrict__ 
     status[FB200_ST_OVERFLOW] = ((long long)status[FB200_ST_NUM_RENDERED] > capacity) ? 1 : 0;
 }
 
+// The tiny-list and small-list sorts are independent and each ends in a long tail (a few long lists on a few SMs);
+// the small-list kernel therefore runs on a side stream, forked after the scatter and joined before the blend.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ready = false;
+};
+
+static SideStream* side_stream() {
+    static SideStream pool[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    SideStream& a = pool[dev];
+    if (!a.ready) {
+        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        a.ready = true;
+    }
+    return &a;
+}
+
 // h_status: the status words of the geometry phase as the HOST has read them (or NULL).  With them the launches
 // that would find an empty work list are skipped (the lists live on the device, so without them every class is
 // launched for the worst case and exits at once).
@@ -482,6 +549,14 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
         count_launch();
     }
     // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides over its list.
+    SideStream* side = (max_tile > kSortTinyMax) ? side_stream() : nullptr;
+    cudaStream_t s2 = s;
+    if (side) {
+        cudaError_t e = cudaEventRecord(side->fork, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+        if (e != cudaSuccess) return e;
+        s2 = side->stream;
+    }
     {
         constexpr int kWarps = 4;                        // 4 x 9 KB of shared memory per CTA
         const int grid = min((T + kWarps - 1) / kWarps, 148 * 6);
@@ -491,7 +566,7 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
     }
     if (max_tile > kSortTinyMax) {
         const int grid = min(T, 148 * 5);
-        tile_sort_shared_kernel<256, kSortSmallMax, false><<<grid, 256, 0, s>>>(
+        tile_sort_shared_kernel<256, kSortSmallMax, false><<<grid, 256, 0, s2>>>(
             a.list_small, a.counters + 0, a.ranges, a.keys, a.point_list, a.status);
         count_launch();
     }
@@ -503,15 +578,20 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (attr != cudaSuccess) return attr;
         const int grid = min(T, 148);
-        tile_sort_shared_kernel<1024, kSortMediumMax, true><<<grid, 1024, smem, s>>>(
+        tile_sort_shared_kernel<1024, kSortMediumMax, true><<<grid, 1024, smem, s2>>>(
             a.list_large, a.counters + 1, a.ranges, a.keys, a.point_list, a.status);
         count_launch();
     }
     if (max_tile > kSortMediumMax) {
         const int grid = min(T, 148 * 2);
-        tile_sort_global_kernel<1024><<<grid, 1024, 0, s>>>(a.list_huge, a.counters + 2, a.ranges, a.keys,
-                                                            a.keys_scratch, a.point_list, a.status);
+        tile_sort_global_kernel<1024><<<grid, 1024, 0, s2>>>(a.list_huge, a.counters + 2, a.ranges, a.keys,
+                                                             a.keys_scratch, a.point_list, a.status);
         count_launch();
+    }
+    if (side) {
+        cudaError_t e = cudaEventRecord(side->join, side->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, side->join, 0);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
