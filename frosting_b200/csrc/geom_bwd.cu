@@ -87,6 +87,12 @@ geom_bwd_kernel(BwdArgs a) {
         return;
     }
     const size_t i = (size_t)(in_range ? idx : 0);
+    if (visible && a.in.d_shs != nullptr && M > 0) {
+        // the SH row is read at the very end of a long dependent chain: start it moving now
+        const char* row = reinterpret_cast<const char*>(a.in.d_shs + i * M * 3);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+        if (M * 12 > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));
+    }
     // SH gradients of a full warp are staged in shared memory and written out coalesced (M == 16)
     const bool stage_sh = full_warp && M == 16 && a.g.d_dL_dsh != nullptr;
     float4* stage = sh_stage[warp] + lane * kShRow;

@@ -41,6 +41,8 @@ struct __align__(16) PairSlabX {
 
 __device__ __forceinline__ P2 ldp(const float* a, int k) { return *reinterpret_cast<const float2*>(a + k); }
 
+// 80 registers / 24 resident warps per SM: measured against 72 / 28 and 64 / 32 (both 5 % slower: more instructions, and
+// the kernel is issue-bound, not latency-bound)
 template <bool kExtra, int kWarps>
 __global__ void __launch_bounds__(32 * kWarps, (kExtra ? 16 : 24) / kWarps)
 render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
