@@ -15,7 +15,7 @@ TILE = 16
 
 # every symbol include/frosting_b200.h declares
 EXPORTED = [
-    "fb200_abi_version", "fb200_last_error", "fb200_geom_bytes", "fb200_image_bytes",
+    "fb200_abi_version", "fb200_abi_struct_sizes", "fb200_last_error", "fb200_geom_bytes", "fb200_image_bytes",
     "fb200_binning_bytes", "fb200_forward", "fb200_forward_geometry", "fb200_forward_raster", "fb200_backward", "fb200_mark_visible",
     "fb200_mesh_visibility", "fb200_gaussian_mask_from_faces", "fb200_get_layout",
     "fb200_profile_enable", "fb200_profile_read", "fb200_kernel_launches",
@@ -175,6 +175,13 @@ def lib():
         getattr(L, n).restype = C.c_int
     if L.fb200_abi_version() != ABI_VERSION:
         raise RuntimeError("frosting_b200: ABI version mismatch between header and library")
+    mirrors = (Params, Inputs, Workspace, Grads, Extra, FrostingParams, FrostingGrads, AdamArgs, Layout)
+    sizes = (C.c_size_t * len(mirrors))()
+    L.fb200_abi_struct_sizes.argtypes = [C.POINTER(C.c_size_t)]
+    L.fb200_abi_struct_sizes.restype = C.c_int
+    if L.fb200_abi_struct_sizes(sizes) != 0 or [int(x) for x in sizes] != [C.sizeof(m) for m in mirrors]:
+        raise RuntimeError("frosting_b200: ctypes struct mirrors out of sync with include/frosting_b200.h: "
+                           f"{[int(x) for x in sizes]} vs {[C.sizeof(m) for m in mirrors]}")
     _lib = L
     return L
 

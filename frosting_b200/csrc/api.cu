@@ -153,6 +153,15 @@ int fb200_profile_read(float* ms_out) {
 int64_t fb200_kernel_launches(void) { return g_launches.load(); }
 
 int fb200_abi_version(void) { return FB200_ABI_VERSION; }
+
+int fb200_abi_struct_sizes(size_t* out) {
+    if (!out) return fail(FB200_EINVAL, "abi_struct_sizes: null output%s");
+    const size_t sizes[FB200_ABI_STRUCTS] = {sizeof(fb200_params), sizeof(fb200_inputs), sizeof(fb200_workspace),
+                                             sizeof(fb200_grads), sizeof(fb200_extra), sizeof(fb200_frosting_params),
+                                             sizeof(fb200_frosting_grads), sizeof(fb200_adam_args), sizeof(fb200_layout)};
+    for (int i = 0; i < FB200_ABI_STRUCTS; ++i) out[i] = sizes[i];
+    return FB200_OK;
+}
 const char* fb200_last_error(void) { return g_err; }
 
 size_t fb200_geom_bytes(int32_t P) { return GeomLayout((size_t)(P < 0 ? 0 : P)).total; }

@@ -304,6 +304,10 @@ int64_t fb200_kernel_launches(void);
 
 const char* fb200_last_error(void);
 int fb200_abi_version(void);
+/* sizeof() of the ABI structs in declaration order {params, inputs, workspace, grads, extra, frosting_params,
+ * frosting_grads, adam_args, layout}: lets a foreign-language binding verify its struct mirrors at load time. */
+#define FB200_ABI_STRUCTS 9
+int fb200_abi_struct_sizes(size_t* out /* [FB200_ABI_STRUCTS] */);
 
 #ifdef __cplusplus
 }
