@@ -91,7 +91,8 @@ class AdamArgs(C.Structure):
                 ("shard_lo", C.c_int64), ("shard_hi", C.c_int64), ("n_groups", C.c_int32),
                 ("group_start", C.c_int64 * (ADAM_MAX_GROUPS + 1)), ("lr", C.c_float * ADAM_MAX_GROUPS),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_float),
-                ("bias_correction1", C.c_float), ("bias_correction2_sqrt", C.c_float), ("grad_scale", C.c_float)]
+                ("bias_correction1", C.c_float), ("bias_correction2_sqrt", C.c_float), ("grad_scale", C.c_float),
+                ("mc_grads", C.c_void_p), ("mc_params", C.c_void_p)]
 
 
 class Layout(C.Structure):

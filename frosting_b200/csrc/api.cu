@@ -427,6 +427,8 @@ int fb200_adam_step(const fb200_adam_args* a, void* stream) {
         for (int p = 0; p < a->world; ++p)
             if (!a->peer_params[p] || !a->peer_grads[p]) return fail(FB200_EINVAL, "adam_step: missing slab pointer%s");
     }
+    if ((a->mc_grads == nullptr) != (a->mc_params == nullptr))
+        return fail(FB200_EINVAL, "adam_step: give both multicast mappings or neither%s");
     if (!(a->bias_correction1 > 0.f) || !(a->bias_correction2_sqrt > 0.f))
         return fail(FB200_EINVAL, "adam_step: bias corrections must be positive (step >= 1)%s");
     return check(launch_adam_shard(*a, static_cast<cudaStream_t>(stream)), "adam_step");

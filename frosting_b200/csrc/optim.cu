@@ -87,6 +87,53 @@ adam_shard_kernel(const fb200_adam_args a) {
     }
 }
 
+// NVLS variant: the same shard walk, but the gradient vector arrives already summed over all ranks -- one
+// multimem.ld_reduce on the multicast mapping of the gradient slabs makes the NVSwitch read every replica and add them --
+// and one multimem.st on the multicast mapping of the parameter slabs makes the switch write every replica.  Per GPU the
+// wire carries shard bytes in and shard bytes out instead of (world - 1) times that.
+__device__ __forceinline__ float4 mc_ld_reduce(const float4* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float4* p, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 4)
+adam_shard_mc_kernel(const fb200_adam_args a) {
+    const int64_t v_lo = a.shard_lo >> 2, v_hi = a.shard_hi >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float4* __restrict__ mom1 = reinterpret_cast<float4*>(a.d_exp_avg);
+    float4* __restrict__ mom2 = reinterpret_cast<float4*>(a.d_exp_avg_sq);
+    const float4* mc_g = reinterpret_cast<const float4*>(a.mc_grads);
+    float4* mc_p = reinterpret_cast<float4*>(a.mc_params);
+    const float4* my_p = reinterpret_cast<const float4*>(a.peer_params[a.rank]);
+    const Coef c{(float)(1.0 - a.beta1), (float)a.beta2, (float)(1.0 - a.beta2), a.bias_correction2_sqrt, a.eps};
+    for (int64_t i = v_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v_hi; i += stride) {
+        float4 s = mc_ld_reduce(mc_g + i);
+        s.x *= a.grad_scale; s.y *= a.grad_scale; s.z *= a.grad_scale; s.w *= a.grad_scale;
+        const int64_t e = i << 2;
+        float lr = a.lr[0];
+#pragma unroll
+        for (int k = 1; k < FB200_ADAM_MAX_GROUPS; ++k)
+            if (k < a.n_groups && e >= a.group_start[k]) lr = a.lr[k];
+        const float step = lr / a.bias_correction1;
+        const int64_t li = i - v_lo;
+        float4 m = mom1[li], v = mom2[li];
+        float4 p = my_p[i];
+        p.x = adam1(s.x, m.x, v.x, p.x, step, c);
+        p.y = adam1(s.y, m.y, v.y, p.y, step, c);
+        p.z = adam1(s.z, m.z, v.z, p.z, step, c);
+        p.w = adam1(s.w, m.w, v.w, p.w, step, c);
+        mom1[li] = m;
+        mom2[li] = v;
+        mc_st(mc_p + i, p);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_adam_shard(const fb200_adam_args& a, cudaStream_t s) {
@@ -97,7 +144,8 @@ cudaError_t launch_adam_shard(const fb200_adam_args& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (vecs + 255) / 256;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);   // 8 resident CTAs of 256 threads per SM
-    if (a.world == 1) adam_shard_kernel<1><<<grid, 256, 0, s>>>(a);
+    if (a.world > 1 && a.mc_grads && a.mc_params) adam_shard_mc_kernel<<<grid, 256, 0, s>>>(a);
+    else if (a.world == 1) adam_shard_kernel<1><<<grid, 256, 0, s>>>(a);
     else if (a.world == 2) adam_shard_kernel<2><<<grid, 256, 0, s>>>(a);
     else if (a.world <= 4) adam_shard_kernel<4><<<grid, 256, 0, s>>>(a);
     else adam_shard_kernel<8><<<grid, 256, 0, s>>>(a);

@@ -113,8 +113,12 @@ class FlatSlabs:
         self.shapes = {n: tuple(tensors[n].shape) for n in names}
         self.starts, self.total = slab_layout([tensors[n].numel() for n in names], world)
         self._owned, self._opened = [], []
+        self.mc_params = self.mc_grads = 0      # NVSwitch multicast mappings of the two slabs (0: none)
+        self.transport = "local"
         L = _lib.lib()
-        if peer:
+        if peer and self._try_symmetric():
+            pass
+        elif peer:
             with torch.cuda.device(self.device):
                 ptrs = []
                 for _ in range(2):
@@ -125,6 +129,7 @@ class FlatSlabs:
                 self.param_slab = _view(ptrs[0], self.total, self.device)
                 self.grad_slab = _view(ptrs[1], self.total, self.device)
                 self.peer_params, self.peer_grads = self._exchange(L, ptrs)
+                self.transport = "cudaIpc peer pointers"
         else:
             self.param_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
             self.grad_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
@@ -135,6 +140,53 @@ class FlatSlabs:
             self.param_slab[s:s + k].copy_(tensors[n].detach().reshape(-1).to(torch.float32))
             self.params[n] = self.param_slab[s:s + k].view(self.shapes[n]).requires_grad_(True)
             self.grads[n] = self.grad_slab[s:s + k].view(self.shapes[n])
+
+    def _try_symmetric(self):
+        """Slabs in torch symmetric memory: peer pointers for every rank AND, on an NVSwitch box, one multicast
+        mapping per slab, which lets the step reduce the gradients in the switch (multimem.ld_reduce) and broadcast
+        the parameters through it (multimem.st).  Every rank must take the same branch, so the outcome is agreed on
+        with an all-reduce; any failure falls back to cudaIpc peer pointers (still CUDA, still one fused kernel)."""
+        import os
+        ok, slabs, handles = 1, [], []
+        if os.environ.get("FB200_NO_SYMM_MEM"):
+            ok = 0
+        else:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                group = self.group if self.group is not None else dist.group.WORLD
+                with torch.cuda.device(self.device):
+                    for _ in range(2):
+                        t = symm.empty(self.total, dtype=torch.float32, device=self.device)
+                        t.zero_()
+                        slabs.append(t)
+                    torch.cuda.synchronize(self.device)
+                    for t in slabs:
+                        handles.append(symm.rendezvous(t, group=group.group_name))
+            except Exception as ex:   # unsupported build / driver / topology
+                self._symm_error = repr(ex)
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return False
+        self._symm_keep = (slabs, handles)
+        self.param_slab, self.grad_slab = slabs
+        out = []
+        for t, h in zip(slabs, handles):
+            base = [int(x) for x in h.buffer_ptrs]
+            off = t.data_ptr() - base[self.rank]            # the tensor's offset inside the symmetric allocation
+            mc = int(getattr(h, "multicast_ptr", 0) or 0)
+            out.append(([b + off for b in base], mc + off if mc else 0))
+        (self.peer_params, self.mc_params), (self.peer_grads, self.mc_grads) = out
+        # multicast must be available on every rank for both slabs
+        flag = torch.tensor([1 if (self.mc_params and self.mc_grads) else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0 or os.environ.get("FB200_NO_MULTICAST"):
+            self.mc_params = self.mc_grads = 0
+            self.transport = "symmetric-memory peer pointers"
+        else:
+            self.transport = "NVSwitch multicast (multimem.ld_reduce / multimem.st)"
+        return True
 
     def _exchange(self, L, ptrs):
         """Trade cudaIpc handles with the other ranks of the box and map their slabs."""
@@ -167,6 +219,7 @@ class FlatSlabs:
             for p in self._owned:
                 L.fb200_peer_free(C.c_void_p(p))
         self._opened, self._owned = [], []
+        self._symm_keep = None
 
 
 class FrostingAdam:
@@ -269,6 +322,8 @@ class FrostingAdam:
         a.bias_correction1 = 1.0 - b1 ** t
         a.bias_correction2_sqrt = math.sqrt(1.0 - b2 ** t)
         a.grad_scale = self.grad_scale
+        a.mc_grads = self.slabs.mc_grads or None
+        a.mc_params = self.slabs.mc_params or None
         return a
 
     def step(self, loss=None):

@@ -254,6 +254,11 @@ typedef struct fb200_adam_args {
     float eps;
     float bias_correction1, bias_correction2_sqrt;
     float grad_scale;
+    /* Optional NVSwitch multicast mappings of the SAME slabs (NVLS; e.g. torch symmetric memory's multicast_ptr), both
+     * or neither.  When given (and world > 1) the gradient shard is summed IN THE SWITCH (multimem.ld_reduce) and the
+     * new parameters are broadcast by the switch (multimem.st): 1/world of the wire bytes of the peer-pointer path. */
+    const float* mc_grads;
+    float* mc_params;
 } fb200_adam_args;
 int fb200_adam_step(const fb200_adam_args* args, void* stream);
 

@@ -58,7 +58,7 @@ def main():
     remote = shard * (world - 1)                 # bytes in (gradients) = bytes out (parameters), per GPU
     hbm = shard * (1 + 3 + 3) + 2 * remote       # own grad + m,v,p reads + m,v,p writes + what the peers read / write here
     if rank == 0:
-        print(f"world {world}: {n / 1e6:.1f} M parameters, {ms:.3f} ms per step; NVLink {remote / 1e6:.0f} MB each way per GPU "
+        print(f"world {world} [{opt.slabs.transport}]: {n / 1e6:.1f} M parameters, {ms:.3f} ms per step; NVLink {remote / 1e6:.0f} MB each way per GPU "
               f"-> {remote / ms / 1e6:.0f} GB/s per direction; local HBM traffic {hbm / 1e6:.0f} MB -> {hbm / ms / 1e6:.0f} GB/s")
     if world > 1:
         dist.barrier()
