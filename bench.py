@@ -512,13 +512,14 @@ def main():
         gts = fstep.gt
         del fstep
         # ... and as a data-parallel TRAINING iteration: gradient reduction over the ranks + Adam (row f3)
-        dp_fps = dp_err = None
+        dp_fps = dp_err = dp_transport = None
         try:
             dstep = OursDPTrainStep(wl, device) if args.impl == "ours" else ReferenceDPTrainStep(wl, device)
             dstep.gt = gts
             secs_d, _, _ = timed_loop(dstep, wl, device, args.steps, args.warmup, world, e2e=False)
             dp_fps = world * args.steps / secs_d
             if args.impl == "ours":
+                dp_transport = dstep.opt.slabs.transport
                 dstep.opt.close()
             del dstep
         except Exception as ex:
@@ -558,6 +559,8 @@ def main():
                                     "note": "secondary: one camera per rank per iteration, loss as above, then gradient mean over "
                                             "the ranks + Adam with the reference's groups (ours: ONE peer-memory reduce+Adam+publish "
                                             "kernel per rank, row f3; reference: NCCL all-reduce of each .grad + torch.optim.Adam)"}
+            if dp_transport:
+                out["dp_train_step"]["transport"] = dp_transport
         else:
             out["dp_train_step_error"] = dp_err
     if clocks:

@@ -181,7 +181,10 @@ class FlatSlabs:
         # multicast must be available on every rank for both slabs
         flag = torch.tensor([1 if (self.mc_params and self.mc_grads) else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        if int(flag.item()) == 0 or os.environ.get("FB200_NO_MULTICAST"):
+        # measured (profiles/r01_dp_adam_kernel_only.txt): the in-switch path costs ~1.1-1.25 ms whatever the world size,
+        # the peer-pointer path 0.76 ms at world 2, 1.11 ms at world 4 and ~1.3 ms at world 8 -> multicast from 4 ranks up
+        want_mc = self.world >= 4 if not os.environ.get("FB200_MULTICAST") else os.environ["FB200_MULTICAST"] == "1"
+        if int(flag.item()) == 0 or not want_mc:
             self.mc_params = self.mc_grads = 0
             self.transport = "symmetric-memory peer pointers"
         else:
