@@ -101,10 +101,11 @@ def _free_port():
     return p
 
 
-def _peer_worker(rank, world, port, q):
+def _peer_worker(rank, world, port, q, multicast):
     import torch.distributed as dist
     from frosting_b200 import optim
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["FB200_MULTICAST"] = "1" if multicast else "0"     # force / forbid the in-switch path at world 2
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -120,26 +121,29 @@ def _peer_worker(rank, world, port, q):
         opt.step(loss=loss)
         loss_sum = float(loss)
     torch.cuda.synchronize(dev)
-    q.put((rank, {n: opt.params[n].detach().cpu().numpy().reshape(-1) for n in SHAPES}, loss_sum))
+    q.put((rank, {n: opt.params[n].detach().cpu().numpy().reshape(-1) for n in SHAPES}, loss_sum, opt.slabs.transport))
     opt.close()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="peer-memory step needs 2 GPUs")
-def test_peer_memory_dp_adam_world2():
+@pytest.mark.parametrize("multicast", [False, True], ids=["peer-pointers", "nvswitch-multicast"])
+def test_peer_memory_dp_adam_world2(multicast):
     import torch.multiprocessing as mp
     from oracle import adam as adam_oracle
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q, multicast)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
     for _ in range(world):
-        r, params, loss_sum = q.get(timeout=300)
+        r, params, loss_sum, transport = q.get(timeout=300)
         res[r] = params
         assert loss_sum == 3.0
+        print("transport:", transport)
+        assert ("multicast" in transport) <= multicast            # never the in-switch path when forbidden
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
