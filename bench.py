@@ -592,8 +592,8 @@ def main():
                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(key), "kernel": key,
                         "kernel_ms": ms, "algorithmic_bytes": bytes_, "peak_source": peaks["src"],
                         "instances_R": R_avg}
-            out["roofline"] = roof(b_bwd, prof["render_bwd"], "render_bwd_kernel")
-            out["roofline_fwd"] = roof(b_fwd, prof["render_fwd"], "render_fwd_kernel")
+            out["roofline"] = roof(b_bwd, prof["render_bwd"], "render_bwd_pair_kernel")
+            out["roofline_fwd"] = roof(b_fwd, prof["render_fwd"], "render_fwd_pair_kernel")
             out["stage_ms"] = prof
         except Exception as ex:   # measurement must not take the headline down with it
             out["roofline_error"] = repr(ex)
