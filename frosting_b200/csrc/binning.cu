@@ -513,6 +513,7 @@ struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     bool ready = false;
+    std::mutex use;     // one fork ... join sequence at a time: the two events are re-recorded by every caller
 };
 
 static SideStream* side_stream() {
@@ -550,6 +551,8 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
     }
     // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides over its list.
     SideStream* side = (max_tile > kSortTinyMax) ? side_stream() : nullptr;
+    std::unique_lock<std::mutex> side_use;
+    if (side) side_use = std::unique_lock<std::mutex>(side->use);
     cudaStream_t s2 = s;
     if (side) {
         cudaError_t e = cudaEventRecord(side->fork, s);
