@@ -45,6 +45,7 @@ WORKLOADS = {
     "tiny": (20_000, 320, 240, 3, "frosting", 1),
 }
 CAMS_PER_GPU = 8
+DP_LEG_TIMEOUT_S = 240
 RING_RADIUS = 10.0
 
 
@@ -511,19 +512,6 @@ def main():
         train_fps = world * args.steps / secs_t
         gts = fstep.gt
         del fstep
-        # ... and as a data-parallel TRAINING iteration: gradient reduction over the ranks + Adam (row f3)
-        dp_fps = dp_err = dp_transport = None
-        try:
-            dstep = OursDPTrainStep(wl, device) if args.impl == "ours" else ReferenceDPTrainStep(wl, device)
-            dstep.gt = gts
-            secs_d, _, _ = timed_loop(dstep, wl, device, args.steps, args.warmup, world, e2e=False)
-            dp_fps = world * args.steps / secs_d
-            if args.impl == "ours":
-                dp_transport = dstep.opt.slabs.transport
-                dstep.opt.close()
-            del dstep
-        except Exception as ex:
-            dp_err = repr(ex)
     H, W, P = wl["H"], wl["W"], wl["P"]
     h2d = 3 * H * W * 4 + (16 + 16 + 3 + 3) * 4
     d2h = 4
@@ -554,15 +542,6 @@ def main():
         out["frosting_train_step"] = {"value": train_fps, "unit": UNIT,
                                       "note": "secondary: parameters -> attributes -> mask -> rasterizer -> 0.8 L1 + 0.2 (1-SSIM) "
                                               "-> backward (ours: fused loss kernel, row f2; reference: its torch loss)"}
-        if dp_fps is not None:
-            out["dp_train_step"] = {"value": dp_fps, "unit": UNIT,
-                                    "note": "secondary: one camera per rank per iteration, loss as above, then gradient mean over "
-                                            "the ranks + Adam with the reference's groups (ours: ONE peer-memory reduce+Adam+publish "
-                                            "kernel per rank, row f3; reference: NCCL all-reduce of each .grad + torch.optim.Adam)"}
-            if dp_transport:
-                out["dp_train_step"]["transport"] = dp_transport
-        else:
-            out["dp_train_step_error"] = dp_err
     if clocks:
         out["clocks"] = clocks
     if args.impl == "reference":
@@ -602,6 +581,42 @@ def main():
                 out["cpu_baseline"], _ = cpu_baseline(wl, step)
             except Exception as ex:
                 out["cpu_baseline_error"] = repr(ex)
+    # ---- last leg: the data-parallel TRAINING iteration (row f3).  It is the only one that maps memory across ranks; it
+    # runs after everything else has been measured and under a watchdog, so a stuck rendezvous cannot take the line down
+    if wl.get("params") is not None:
+        import threading
+        lock, finished = threading.Lock(), [False]
+
+        def bail():
+            with lock:
+                if finished[0]:
+                    return
+                out["dp_train_step_error"] = f"timeout: leg abandoned after {DP_LEG_TIMEOUT_S} s"
+                if rank == 0:
+                    os.write(result_fd, (json.dumps(out) + "\n").encode())
+                os._exit(0)
+
+        timer = threading.Timer(DP_LEG_TIMEOUT_S, bail)
+        timer.daemon = True
+        timer.start()
+        try:
+            dstep = OursDPTrainStep(wl, device) if args.impl == "ours" else ReferenceDPTrainStep(wl, device)
+            dstep.gt = gts
+            secs_d, _, _ = timed_loop(dstep, wl, device, args.steps, args.warmup, world, e2e=False)
+            out["dp_train_step"] = {
+                "value": world * args.steps / secs_d, "unit": UNIT,
+                "note": "secondary: one camera per rank per iteration, loss as above, then gradient mean over the ranks + Adam "
+                        "with the reference's groups (ours: ONE peer-memory reduce+Adam+publish kernel per rank, row f3; "
+                        "reference: NCCL all-reduce of each .grad + torch.optim.Adam)"}
+            if args.impl == "ours":
+                out["dp_train_step"]["transport"] = dstep.opt.slabs.transport
+                dstep.opt.close()
+            del dstep
+        except Exception as ex:
+            out["dp_train_step_error"] = repr(ex)
+        with lock:
+            finished[0] = True
+        timer.cancel()
     if rank == 0:
         os.write(result_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
