@@ -11,7 +11,7 @@ where the numbers live and how ranks exchange them:
 * under `torch.distributed` with world > 1 both slabs are peer-mapped (torch symmetric memory, else cudaIpc handles
   exchanged once through `all_gather_object`) and `step()` launches `fb200_adam_step`: each rank reduces ITS 1/world shard of the gradients
   out of all ranks' slabs over NVLink, updates its shard of the Adam moments, and stores the new parameters into
-  every rank's slab -- gradient all-reduce, optimizer and parameter broadcast in one kernel; from 4 ranks up the sum
+  every rank's slab -- gradient all-reduce, optimizer and parameter broadcast in one kernel; at 4 ranks the sum
   is formed in the NVSwitch (multimem.ld_reduce on the slabs' multicast mapping) and the parameters are broadcast by
   it (multimem.st).  The two rendezvous it needs are 4-byte NCCL all-reduces (the first one carries the scalar loss);
 * world == 1: the same kernel as a plain fused multi-group Adam.
