@@ -577,8 +577,9 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
         // medium lists (2048 < n <= 8192): 1024 threads, ping-pong buffers + per-warp counters in 160 KB of
         // dynamic shared memory, one CTA per SM
         const int smem = 2 * 8 * kSortMediumMax + 32 * 256 * 4;
-        static const cudaError_t attr = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortMediumMax, true>,
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // per call, not once per process: the attribute is per device
+        const cudaError_t attr = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortMediumMax, true>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (attr != cudaSuccess) return attr;
         const int grid = min(T, 148);
         tile_sort_shared_kernel<1024, kSortMediumMax, true><<<grid, 1024, smem, s2>>>(
