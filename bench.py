@@ -1,30 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- forward+backward frames/sec of the render path on BASELINE.json's headline config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5] [--quick]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config C3 of BASELINE.json): 2 M frosting-layer Gaussians bound to the prism cells of a ~1 M-face
-UV-sphere shell (frosting_b200/scenes.py), occlusion culling ON, 1920x1080, SH degree 3, synthetic data,
-random-init parameters.  A "step" is one frame: occlusion mask -> rasterizer forward -> scalar loss
-(color * G).sum() -> backward to means3D / SH / opacity / scale / rotation (+ the means2D sink), for one
-camera; every rank owns 8 cameras on a ring (config C4's sharding: camera batch split across GPUs, Gaussians
-replicated, the only collective is the NCCL all-reduce of the scalar loss) and cycles through them, so
-per-GPU work is fixed as N grows ("weak" scaling).  `value` = frames all ranks finished / max-over-ranks time.
+UV-sphere shell (frosting_b200/scenes.py), occlusion culling ON, 1920x1080, SH degree 3, ring of cameras of radius 6
+(SURVEY.md 8d), synthetic data, random-init parameters.  A "step" is one frame: occlusion mask -> rasterizer forward
+-> scalar loss (color * G).sum() -> backward to means3D / SH / opacity / scale / rotation (+ the means2D sink), for one
+camera; every rank owns 8 cameras of the ring (config C4's sharding: camera batch split across GPUs, Gaussians
+replicated, the only collective is the NCCL all-reduce of the scalar loss) and cycles through them, so per-GPU work
+is fixed as N grows ("weak" scaling).  `value` = frames all ranks finished / max-over-ranks time.  The frame loop is
+frosting_b200.camera_batch.CameraBatch (package API); this file only times it.
 
 --impl reference runs the UNMODIFIED reference rasterizer compiled from /root/reference into oracle/_ref
 (oracle/build_ref.py) through its own entry points, with Frosting's boolean-gather masking
-(frosting_scene/frosting_model.py:1564-1586) in torch, on the same scene, cameras and loss.  The reference
-has no CPU implementation of this path; its own CUDA code is the stock code path.
+(frosting_scene/frosting_model.py:1564-1586) in torch, on the same scene, cameras and loss.  The reference has no CPU
+implementation of this path; its own CUDA code is the stock code path.  That process never maps
+libfrosting_b200.so: the visible-face sets (the prepass the reference gets from nvdiffrast, absent here) are computed by
+a CHILD process before anything is timed and handed over in a file.
 
-Timing: CUDA events around exactly K steps after W warm-up steps, barrier + synchronize on both sides, max
-over ranks.  Inputs are larger than L2 (472 MB of attributes are read per frame, 126 MB L2), no flush needed.
+Sub-blocks of the JSON line (N = 1 only, each with the shipped kernels): `dropin` (Frosting's boolean gathers in torch
++ our rasterizer, no API extension), `c2`, `c5` (BASELINE configs 2 and 5, with their own roofline), `c3_ring10`
+(round 1's camera distance), `prepass_ms` (the occlusion prepass at 1 M faces / 1080p), `frosting_step`,
+`frosting_train_step`, `dp_train_step` (+ `dp_check`).
+
+Timing: CUDA events around exactly K steps after W warm-up steps, barrier + synchronize on both sides, max over
+ranks.  Inputs are larger than L2 (472 MB of attributes are read per frame, 126 MB L2), no flush needed.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -34,19 +43,12 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from frosting_b200 import camera_batch as cb   # noqa: E402  (imports no native code)
+
 METRIC = "fwd+bwd frames/sec @2M Gaussians 1080p"
 UNIT = "frames/s"
-
-WORKLOADS = {
-    # name: (P, W, H, sh_degree, kind, seed)
-    "c3": (2_000_000, 1920, 1080, 3, "frosting", 1237),
-    "c2": (500_000, 800, 800, 3, "random", 1236),
-    "c5": (6_000_000, 1600, 1200, 3, "random", 1239),
-    "tiny": (20_000, 320, 240, 3, "frosting", 1),
-}
-CAMS_PER_GPU = 8
 DP_LEG_TIMEOUT_S = 240
-RING_RADIUS = 10.0
+RING_RADIUS = float(os.environ.get("FB200_RING_RADIUS", str(cb.RING_RADIUS)))
 
 
 def log(*a):
@@ -99,159 +101,62 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(name, device, rank, world):
-    from frosting_b200 import scenes
-    P, W, H, D, kind, seed = WORKLOADS[name]
-    n_cams = CAMS_PER_GPU * world
-    cam0 = scenes.make_camera(W, H, device=device)
-    if kind == "frosting":
-        # ring of radius 10 around the shell (radius 3): the whole object is in frame, ~26 % of the Gaussians
-        # survive occlusion culling, R ~ 1.6 M tile instances per frame
-        cams = scenes.ring_cameras(n_cams, W, H, radius=RING_RADIUS, device=device)[
-            rank * CAMS_PER_GPU:(rank + 1) * CAMS_PER_GPU]
-    else:
-        cams = [cam0] * CAMS_PER_GPU   # free Gaussians are generated inside cam0's frustum
-    wl = dict(name=name, P=P, W=W, H=H, D=D, kind=kind, cams=cams)
-    t = time.time()
-    if kind == "frosting":
-        params, mesh = scenes.frosting_layer(P, cam0, seed, n_faces_target=max(1000, P // 2), device="cpu")
-        attrs = scenes.frosting_attributes(params, mesh)
-        wl["mesh"] = {k: v.to(device) for k, v in mesh.items()}
-        wl["params"] = {k: v.to(device) for k, v in params.items()}
-    else:
-        attrs = scenes.random_gaussians(P, cam0, seed, device="cpu")
-        # spread the free Gaussians around the ring centre so every ring camera sees a similar load
-        wl["mesh"] = None
-    wl["attrs"] = {k: v.to(device).contiguous() for k, v in attrs.items()}
-    g = torch.Generator().manual_seed(4321 + rank)
-    wl["cot_host"] = [torch.randn(3, H, W, generator=g).pin_memory() for _ in range(len(cams))]
-    # per-camera host record (pinned): viewmatrix 16 | projmatrix 16 | campos 3 | bg 3 -- what Frosting builds on
-    # the CPU every call and uploads (frosting_model.py:1420-1444)
-    wl["cam_host"] = [torch.cat([c.world_view_transform.reshape(-1).cpu(), c.full_proj_transform.reshape(-1).cpu(),
-                                 c.camera_center.reshape(-1).cpu(), torch.zeros(3)]).float().pin_memory() for c in cams]
-    wl["gen_s"] = time.time() - t
-    return wl
+# ---- the reference arm -----------------------------------------------------------------------------------------------
+def visible_faces_in_child(name, rank, world, ring_radius, local_rank):
+    """The reference arm must not map libfrosting_b200.so: a child process runs the CUDA prepass (the stand-in for
+    nvdiffrast) for this rank's cameras and leaves the visible-face sets in a file."""
+    fd, path = tempfile.mkstemp(suffix=".pt", prefix="fb200_vis_")
+    os.close(fd)
+    code = ("import sys, torch; sys.path.insert(0, %r); from frosting_b200 import camera_batch as cb; "
+            "dev = torch.device('cuda', %d); torch.cuda.set_device(dev); "
+            "wl = cb.build_workload(%r, dev, %d, %d, ring_radius=%r); "
+            "torch.save([v.cpu() for v in cb.visible_faces(wl)], %r)"
+            % (ROOT, local_rank, name, rank, world, ring_radius, path))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL, env=env)
+    vis = torch.load(path)
+    os.unlink(path)
+    return vis
 
 
-def precompute_visibility(wl, device):
-    """Visible-face set per camera, once, as Frosting's refinement does (frosting_trainers/refine.py:430-441)."""
-    import frosting_b200 as fb
-    if wl["mesh"] is None:
-        wl["face_visible"] = None
-        return
-    vis = []
-    for cam in wl["cams"]:
-        _, fv, _ = fb.rasterize_mesh(wl["mesh"]["verts"], wl["mesh"]["faces"], cam.full_proj_transform,
-                                     cam.image_height, cam.image_width, mark_last_on_bg=True)
-        vis.append(fv.to(torch.uint8).contiguous())
-    wl["face_visible"] = vis
+class ReferenceBatch:
+    """The reference arm's frames: the reference's own chain, nothing of this repo's native code.
+    mode "raster": attributes -> boolean gathers (frosting_model.py:1564-1586) -> reference rasterizer -> loss -> backward
+    mode "frosting": torch property ops (frosting_model.py:713-799, restated in scenes.frosting_attributes) first;
+    loss "l1_dssim": the reference's torch loss (frosting_utils/loss_utils.py:17-63, restated in loss.torch_reference)."""
 
-
-class OursStep:
-    def __init__(self, wl, device):
-        import frosting_b200 as fb
-        from frosting_b200 import scenes
-        self.fb, self.scenes, self.wl, self.device = fb, scenes, wl, device
-        self.leaves = {k: v.clone().requires_grad_(True) for k, v in wl["attrs"].items()}
-        self.P = wl["P"]
-        self.last_R = 0
-
-    def settings(self, cam):
-        return self.scenes.settings_for(cam, self.wl["D"], device=self.device)
-
-    def __call__(self, i, rs, cot):
-        fb, L = self.fb, self.leaves
-        for v in L.values():
-            v.grad = None                                        # zero_grad(set_to_none=True), refine.py:522
-        mask = None
-        if self.wl["face_visible"] is not None:
-            mask = fb.gaussian_render_mask(self.wl["face_visible"][i], self.wl["mesh"]["cells"], self.P)
-        means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)   # frosting_model.py:1624
-        color, radii = fb.GaussianRasterizer(rs)(
-            means3D=L["means3D"], means2D=means2D, opacities=L["opacities"], shs=L["shs"], scales=L["scales"],
-            rotations=L["rotations"], visibility_mask=mask)
-        loss = (color * cot).sum()
-        loss.backward()
-        return loss.detach()
-
-
-class ReferenceStep:
-    def __init__(self, wl, device):
+    def __init__(self, wl, device, mode="raster", loss="cot"):
         from oracle import refdgr
         from frosting_b200 import scenes
         refdgr.module()
         self.refdgr, self.scenes, self.wl, self.device = refdgr, scenes, wl, device
-        self.leaves = {k: v.clone().requires_grad_(True) for k, v in wl["attrs"].items()}
-        self.masks = None
-        if wl["face_visible"] is not None:
-            self.cells = wl["mesh"]["cells"]
+        self.mode, self.loss_mode = mode, loss
+        if mode == "raster":
+            self.leaves = {k: v.clone().requires_grad_(True) for k, v in wl["attrs"].items()}
+        else:
+            self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
+        self.cells = wl["mesh"]["cells"] if wl["mesh"] is not None else None
+        self.gt = None
 
     def settings(self, cam):
         return self.scenes.settings_for(cam, self.wl["D"], device=self.device)
 
-    def __call__(self, i, rs, cot):
-        L = self.leaves
-        for v in L.values():
-            v.grad = None
-        m3, op, sh, sc, ro = L["means3D"], L["opacities"], L["shs"], L["scales"], L["rotations"]
+    def frame(self, i, rs, cot):
+        if self.mode == "raster":
+            a = self.leaves
+            for v in a.values():
+                v.grad = None
+        else:
+            for v in self.params.values():
+                v.grad = None
+            a = self.scenes.frosting_attributes(self.params, self.wl["mesh"])
+        m3, op, sh, sc, ro = (a[k] for k in ("means3D", "opacities", "shs", "scales", "rotations"))
         if self.wl["face_visible"] is not None:
-            # frosting_model.py:1564-1586: _index_mask[_point_cell_indices], then boolean gathers
             render_mask = self.wl["face_visible"][i].bool()[self.cells]
             m3, op, sh, sc, ro = m3[render_mask], op[render_mask], sh[render_mask], sc[render_mask], ro[render_mask]
         means2D = torch.zeros_like(m3, requires_grad=True)
         color, radii = self.refdgr.RefRasterize.apply(m3, means2D, sh, op, sc, ro, rs)
-        loss = (color * cot).sum()
-        loss.backward()
-        return loss.detach()
-
-
-class OursFrostingStep(OursStep):
-    """Frame as Frosting's refinement loop sees it (refine.py:487-518): learnable parameters -> attributes (row a20,
-    fused kernel) -> occlusion mask -> rasterizer -> loss -> backward down to the parameters."""
-
-    def __init__(self, wl, device):
-        super().__init__(wl, device)
-        self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
-        self.real_loss = False
-        self.gt = None
-
-    def __call__(self, i, rs, cot):
-        fb = self.fb
-        for v in self.params.values():
-            v.grad = None
-        mask = fb.gaussian_render_mask(self.wl["face_visible"][i], self.wl["mesh"]["cells"], self.P)
-        a = fb.frosting_attributes_fused(self.params, self.wl["mesh"], mask)
-        means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
-        color, radii = fb.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=means2D, opacities=a["opacities"],
-                                                 shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
-                                                 visibility_mask=mask)
-        if self.real_loss:
-            loss = fb.l1_dssim_loss(color, self.gt[i], 0.2)          # fused L1 + D-SSIM (row f2)
-        else:
-            loss = (color * cot).sum()
-        loss.backward()
-        return loss.detach()
-
-
-class ReferenceFrostingStep(ReferenceStep):
-    """Same frame through the reference's own chain: torch property ops (frosting_model.py:713-799), boolean
-    gathers (:1564-1586), reference rasterizer."""
-
-    def __init__(self, wl, device):
-        super().__init__(wl, device)
-        self.params = {k: v.clone().requires_grad_(True) for k, v in wl["params"].items()}
-        self.real_loss = False
-        self.gt = None
-
-    def __call__(self, i, rs, cot):
-        for v in self.params.values():
-            v.grad = None
-        a = self.scenes.frosting_attributes(self.params, self.wl["mesh"])
-        render_mask = self.wl["face_visible"][i].bool()[self.cells]
-        m3, op, sh, sc, ro = (a[k][render_mask] for k in ("means3D", "opacities", "shs", "scales", "rotations"))
-        means2D = torch.zeros_like(m3, requires_grad=True)
-        color, radii = self.refdgr.RefRasterize.apply(m3, means2D, sh, op, sc, ro, rs)
-        if self.real_loss:
+        if self.loss_mode == "l1_dssim":
             from frosting_b200.loss import torch_reference     # restates frosting_utils/loss_utils.py:17-63 verbatim
             loss = torch_reference(color, self.gt[i], 0.2)
         else:
@@ -260,7 +165,7 @@ class ReferenceFrostingStep(ReferenceStep):
         return loss.detach()
 
 
-class OursDPTrainStep(OursFrostingStep):
+class OursDPTrain(cb.CameraBatch):
     """One data-parallel TRAINING iteration (row f3): every rank renders its camera from the shared parameters
     (fused attributes -> mask -> rasterizer -> fused L1 + D-SSIM -> backward writing into the gradient slab), then ONE
     kernel per rank reduces its shard of all ranks' gradients over NVLink peer memory, applies Adam (the reference's
@@ -268,44 +173,33 @@ class OursDPTrainStep(OursFrostingStep):
     handles_collective = True
 
     def __init__(self, wl, device):
-        super().__init__(wl, device)
-        self.opt = self.fb.FrostingAdam.for_frosting(wl["params"])
-        self.params = self.opt.params
-        self.real_loss = True
+        import frosting_b200 as fb
+        opt = fb.FrostingAdam.for_frosting(wl["params"])
+        super().__init__(wl, device, mode="frosting", mask="fused", loss="l1_dssim", optimizer=opt)
 
-    def __call__(self, i, rs, cot):
-        fb = self.fb
-        mask = fb.gaussian_render_mask(self.wl["face_visible"][i], self.wl["mesh"]["cells"], self.P)
-        a = fb.frosting_attributes_fused(self.params, self.wl["mesh"], mask, grad_sink=self.opt.grads)
-        means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
-        color, radii = fb.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=means2D, opacities=a["opacities"],
-                                                 shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
-                                                 visibility_mask=mask)
-        loss = fb.l1_dssim_loss(color, self.gt[i], 0.2)
-        loss.backward()
-        loss = loss.detach().reshape(1).clone()
+    def frame(self, i, rs, cot):
+        loss = super().frame(i, rs, cot).reshape(1).clone()
         self.opt.update_learning_rate()
         self.opt.step(loss=loss)            # the loss all-reduce doubles as the pre-step rendezvous
         return loss
 
 
-class ReferenceDPTrainStep(ReferenceFrostingStep):
+class ReferenceDPTrain(ReferenceBatch):
     """What a torch user gets from the reference today: its render chain, NCCL all-reduce of every .grad (averaged),
     torch.optim.Adam(lr=0.0, eps=1e-15) over the same groups (frosting_optimizer.py:74-101,116-118)."""
     handles_collective = True
 
     def __init__(self, wl, device):
-        super().__init__(wl, device)
+        super().__init__(wl, device, mode="frosting", loss="l1_dssim")
         from frosting_b200.optim import OptimizationParams
         o = OptimizationParams()
         lr = {"bary_logits": o.position_bary_coords_lr_init, "sh_dc": o.feature_lr, "sh_rest": o.feature_lr / 20.0,
               "opacity_logits": o.opacity_lr, "log_scales": o.scaling_lr, "quats": o.rotation_lr}
         self.opt = torch.optim.Adam([{"params": [self.params[k]], "lr": lr[k], "name": k} for k in lr], lr=0.0, eps=1e-15)
-        self.real_loss = True
         self.world = dist.get_world_size() if dist.is_initialized() else 1
 
-    def __call__(self, i, rs, cot):
-        loss = super().__call__(i, rs, cot).reshape(1).clone()
+    def frame(self, i, rs, cot):
+        loss = super().frame(i, rs, cot).reshape(1).clone()
         if self.world > 1:
             dist.all_reduce(loss)
             for v in self.params.values():
@@ -315,7 +209,8 @@ class ReferenceDPTrainStep(ReferenceFrostingStep):
         return loss
 
 
-def timed_loop(step, wl, device, steps, warmup, world, e2e):
+# ---- timing ----------------------------------------------------------------------------------------------------------
+def timed_loop(step, wl, device, steps, warmup, world, e2e, count_launches=False):
     """Returns seconds for exactly `steps` steps (max over ranks)."""
     cams = wl["cams"]
     n = len(cams)
@@ -324,6 +219,7 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
     if not e2e:
         rs_dev = [step.settings(c) for c in cams]
         cot_dev = [c.to(device) for c in wl["cot_host"]]
+    own_collective = getattr(step, "handles_collective", False)
 
     def fetch(i):
         """H2D of step inputs from pinned host memory on the copy stream (double-buffered)."""
@@ -340,6 +236,9 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
 
     def run(k_steps, offset):
         losses = []
+        # the path's only collective: every frame's scalar loss is summed over the ranks by its own asynchronous NCCL
+        # all-reduce; the compute stream never waits for it, the results are collected before the timed region ends
+        reducer = cb.LossReducer() if (world > 1 and not own_collective) else None
         pending = None                      # (pinned slot, event) of the previous step's loss read-back
         nxt = fetch(offset) if e2e else None
         for k in range(k_steps):
@@ -353,9 +252,9 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
                     nxt = fetch(offset + k + 1)
             else:
                 rs, cot = rs_dev[i], cot_dev[i]
-            loss = step(i, rs, cot)
-            if world > 1 and not getattr(step, "handles_collective", False):
-                dist.all_reduce(loss)                      # the path's only collective: scalar loss over NVLink
+            loss = step.frame(i, rs, cot)
+            if reducer is not None:
+                reducer.add(loss)
             if e2e:
                 # D2H read of the step's result, every step: async copy into pinned memory, consumed one step later so
                 # the read-back of step k overlaps step k+1 instead of draining the GPU (losses lag by one step, as an
@@ -370,6 +269,8 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
         if e2e and pending is not None:
             pending[1].synchronize()
             losses.append(float(pending[0][0]))
+        if reducer is not None:
+            reducer.collect()
         return losses
 
     if not getattr(step, "primed", False):
@@ -382,14 +283,17 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
         dist.barrier()
     torch.cuda.synchronize(device)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    from frosting_b200 import _lib
-    l0 = _lib.kernel_launches()
+    l0 = 0
+    if count_launches:
+        from frosting_b200 import _lib
+        l0 = _lib.kernel_launches()
     t0 = time.time()
     a.record()
     run(steps, warmup)
     b.record()
     torch.cuda.synchronize(device)
-    timed_loop.launches = _lib.kernel_launches() - l0
+    if count_launches:
+        timed_loop.launches = _lib.kernel_launches() - l0
     if world > 1:
         dist.barrier()
     t1 = time.time()
@@ -404,23 +308,50 @@ def timed_loop(step, wl, device, steps, warmup, world, e2e):
 def stage_profile(step, wl, device, steps):
     """Average device time of each kernel stage (CUDA events on the launching stream, inside the library)."""
     from frosting_b200 import _lib
+    import frosting_b200 as fb
     cams = wl["cams"]
     rs_dev = [step.settings(c) for c in cams]
     cot_dev = [c.to(device) for c in wl["cot_host"]]
     _lib.profile_enable(True)
     acc = {k: 0.0 for k in _lib.STAGES}
-    Rs = []
+    Rs, Vs = [], []
     try:
         for k in range(steps):
             i = k % len(cams)
-            step(i, rs_dev[i], cot_dev[i])
+            step.frame(i, rs_dev[i], cot_dev[i])
             torch.cuda.synchronize(device)
             for kk, v in _lib.profile_read().items():
                 acc[kk] += v
-            Rs.append(int(step.fb.rasterizer.last_num_rendered()))
+            Rs.append(int(fb.rasterizer.last_num_rendered(device)))
+            Vs.append(int((step.last["radii"] > 0).sum()))
     finally:
         _lib.profile_enable(False)
-    return {k: v / steps for k, v in acc.items()}, sum(Rs) / len(Rs)
+    return {k: v / steps for k, v in acc.items()}, sum(Rs) / len(Rs), sum(Vs) / len(Vs)
+
+
+def rooflines(prof, R_avg, W, H, workload):
+    """algorithmic bytes of the blend kernels / their live CUDA-event time vs the measured HBM peak."""
+    peaks = {"hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = {"hbm_gbs": float(json.load(open(pk))["hbm_gbs"]), "src": "measured"}
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    Npx = H * W
+    b_fwd = 40 * R_avg + 20 * Npx + 8 * T + 12
+    b_bwd = 76 * R_avg + 20 * Npx + 8 * T + 12
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(workload, {})
+
+    def roof(bytes_, ms, key):
+        ach = bytes_ / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(key), "kernel": key,
+                "kernel_ms": ms, "algorithmic_bytes": bytes_, "peak_source": peaks["src"],
+                "instances_R": R_avg}
+    return (roof(b_bwd, prof["render_bwd"], traffic.get("bwd_kernel_name", "render_bwd_pair_kernel")),
+            roof(b_fwd, prof["render_fwd"], traffic.get("fwd_kernel_name", "render_fwd_pair_kernel")))
 
 
 def cpu_baseline(wl, step, sample_cam=0):
@@ -444,14 +375,74 @@ def cpu_baseline(wl, step, sample_cam=0):
                        f"single thread, {dt:.1f} s"), f["binned"]["num_rendered"]
 
 
+def make_step(impl, wl, device, **kw):
+    if impl == "ours":
+        return cb.CameraBatch(wl, device, **kw)
+    kw.pop("mask", None)
+    return ReferenceBatch(wl, device, **kw)
+
+
+def load_workload(name, device, rank, world, impl, local_rank, ring_radius):
+    wl = cb.build_workload(name, device, rank, world, ring_radius=ring_radius)
+    if wl["mesh"] is not None:
+        if impl == "ours":
+            cb.visible_faces(wl)
+        else:
+            wl["face_visible"] = [v.to(device) for v in visible_faces_in_child(name, rank, world, ring_radius, local_rank)]
+    return wl
+
+
+def side_config(name, impl, device, steps, warmup, local_rank, ring_radius=RING_RADIUS):
+    """A secondary BASELINE config on one GPU: value (+ stage times and rooflines for our arm)."""
+    wl = load_workload(name, device, 0, 1, impl, local_rank, ring_radius)
+    step = make_step(impl, wl, device)
+    secs, _, _ = timed_loop(step, wl, device, steps, warmup, 1, e2e=False)
+    out = {"value": steps / secs, "unit": UNIT, "ms_per_step": 1e3 * secs / steps, "steps": steps,
+           "workload": cb.WORKLOAD_TEXT[name] + (f", ring radius {ring_radius:g}" if wl["kind"] == "frosting" else "")}
+    if impl == "ours":
+        prof, R_avg, V_avg = stage_profile(step, wl, device, min(steps, 8))
+        out["roofline"], out["roofline_fwd"] = rooflines(prof, R_avg, wl["W"], wl["H"], name)
+        out["stage_ms"] = prof
+        out["scene"] = {"P": wl["P"], "V": V_avg, "R": R_avg, "R_over_P": R_avg / wl["P"]}
+    del step, wl
+    torch.cuda.empty_cache()
+    return out
+
+
+def prepass_ms(wl, device, reps=10):
+    """The occlusion prepass alone (row a19): ~1 M faces rasterised at 1080p + the Gaussian mask, per frame, as
+    Frosting's inference path runs it (frosting_model.py:1524-1539)."""
+    import frosting_b200 as fb
+    cam = wl["cams"][0]
+    m = wl["mesh"]
+
+    def once():
+        _, fv, _ = fb.rasterize_mesh(m["verts"], m["faces"], cam.full_proj_transform, cam.image_height, cam.image_width,
+                                     mark_last_on_bg=True)
+        return fb.gaussian_render_mask(fv.to(torch.uint8), m["cells"], wl["P"])
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        once()
+    b.record()
+    torch.cuda.synchronize(device)
+    return {"value": a.elapsed_time(b) / reps, "unit": "ms", "faces": int(m["faces"].shape[0]),
+            "image": f"{cam.image_width}x{cam.image_height}",
+            "note": "mesh raster (z-buffer atomics + resolve + visible-face marks) + face_visible[cell] mask, per frame"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(cb.WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="developer runs: headline + stage profile only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: route fd 1 to stderr for the whole run (NCCL / C libraries print their
@@ -472,8 +463,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     if args.gpus != world and rank == 0:
         log(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: using WORLD_SIZE")
+    ours = args.impl == "ours"
 
-    if args.impl == "reference":
+    if not ours:
         from oracle import refdgr
         if not refdgr.available():
             if rank == 0:
@@ -481,51 +473,36 @@ def main():
                                                  "oracle/_ref/ref_dgr_C.so not built (needs /root/reference)"}) + "\n").encode())
             return
 
-    import frosting_b200 as fb
-    from frosting_b200 import _lib
-    wl = build_workload(args.workload, device, rank, world)
-    precompute_visibility(wl, device)
-    step = OursStep(wl, device) if args.impl == "ours" else ReferenceStep(wl, device)
+    wl = load_workload(args.workload, device, rank, world, args.impl, local_rank, RING_RADIUS)
+    step = make_step(args.impl, wl, device)
     log(f"[bench] rank {rank}: workload {args.workload} built in {wl['gen_s']:.1f}s, impl={args.impl}")
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    secs, t0, t1 = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=False)
+    secs, t0, t1 = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=False, count_launches=ours)
     clocks = sampler.stop(t0, t1) if sampler else None
-    launches_timed = timed_loop.launches   # kernels of libfrosting_b200.so launched inside the timed region
+    launches_timed = timed_loop.launches if ours else 0   # kernels of libfrosting_b200.so launched inside the timed region
     value = world * args.steps / secs
 
-    secs_e2e, _, _ = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=True)
-    e2e_value = world * args.steps / secs_e2e
-    frosting_fps = None
-    if wl.get("params") is not None:
-        fstep = OursFrostingStep(wl, device) if args.impl == "ours" else ReferenceFrostingStep(wl, device)
-        secs_f, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
-        frosting_fps = world * args.steps / secs_f
-        # ... and with the trainers' real loss, 0.8 L1 + 0.2 (1 - SSIM) against a ground-truth image (refine.py:407-409)
-        gtg = torch.Generator().manual_seed(99 + rank)
-        fstep.gt = [torch.rand(3, wl["H"], wl["W"], generator=gtg).to(device) for _ in wl["cams"]]
-        fstep.real_loss = True
-        fstep.primed = False
-        secs_t, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
-        train_fps = world * args.steps / secs_t
-        gts = fstep.gt
-        del fstep
+    e2e_value = None
+    if not args.quick:
+        secs_e2e, _, _ = timed_loop(step, wl, device, args.steps, args.warmup, world, e2e=True)
+        e2e_value = world * args.steps / secs_e2e
     H, W, P = wl["H"], wl["W"], wl["P"]
     h2d = 3 * H * W * 4 + (16 + 16 + 3 + 3) * 4
     d2h = 4
+    ring_txt = f", ring radius {RING_RADIUS:g}" if wl["kind"] == "frosting" else ""
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": {"c3": "C3: 2M frosting-layer Gaussians (mesh-bound prism cells, occlusion culling ON), "
-                               "1920x1080, SH degree 3", "c2": "C2: 500k random Gaussians 800x800 SH3",
-                         "c5": "C5: 6M random Gaussians 1600x1200 SH3", "tiny": "tiny smoke workload"}[args.workload],
-            "gaussians": P, "image": f"{W}x{H}", "sh_degree": wl["D"], "cameras_per_gpu": CAMS_PER_GPU,
-            "parallelism": f"camera-batch x{world} (Gaussians replicated, NCCL all-reduce of the scalar loss)",
+            "workload": cb.WORKLOAD_TEXT[args.workload] + ring_txt,
+            "gaussians": P, "image": f"{W}x{H}", "sh_degree": wl["D"], "cameras_per_gpu": cb.CAMS_PER_GPU,
+            "parallelism": f"camera-batch x{world} (Gaussians replicated, NCCL all-reduce of the scalar loss, "
+                           "asynchronous per frame)",
             "frame": "occlusion mask + rasterizer forward + (color*G).sum() + backward to all attributes",
             "l2": "inputs larger than L2: ~236 B x P of attributes read per frame, no flush needed",
         },
@@ -535,56 +512,64 @@ def main():
                         "stay resident as in the reference"},
         "gpu_launches": launches_timed,
     }
-    if frosting_fps is not None:
-        out["frosting_step"] = {"value": frosting_fps, "unit": UNIT,
-                                "note": "secondary: the same frame starting from Frosting's learnable parameters "
-                                        "(attribute construction, row a20, inside the step)"}
-        out["frosting_train_step"] = {"value": train_fps, "unit": UNIT,
-                                      "note": "secondary: parameters -> attributes -> mask -> rasterizer -> 0.8 L1 + 0.2 (1-SSIM) "
-                                              "-> backward (ours: fused loss kernel, row f2; reference: its torch loss)"}
     if clocks:
         out["clocks"] = clocks
-    if args.impl == "reference":
+    if not ours:
         out["impl"] = "reference"
         out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                                "sample": "the reference's own CUDA rasterizer (oracle/_ref, built from /root/reference) "
                                          "on the GPU: the reference has no CPU implementation of this path"}
+        out["reference_notes"] = ("visible-face sets come from a child process (this process maps no repo library); "
+                                  "frosting_step / frosting_train_step / dp_train_step use this repo's torch RESTATEMENTS of "
+                                  "the reference's property chain and loss (scenes.frosting_attributes, loss.torch_reference)")
     else:
         try:
-            prof, R_avg = stage_profile(step, wl, device, min(args.steps, 16))
-            peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
-            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-            if os.path.exists(pk):
-                peaks = {"hbm_gbs": float(json.load(open(pk))["hbm_gbs"]), "src": "measured"}
-            T = ((W + 15) // 16) * ((H + 15) // 16)
-            Npx = H * W
-            b_fwd = 40 * R_avg + 20 * Npx + 8 * T + 12
-            b_bwd = 76 * R_avg + 20 * Npx + 8 * T + 12
-            traffic = {}
-            tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-            if os.path.exists(tp):
-                traffic = json.load(open(tp)).get(args.workload, {})
-
-            def roof(bytes_, ms, key):
-                ach = bytes_ / (ms * 1e-3) / 1e9
-                return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(key), "kernel": key,
-                        "kernel_ms": ms, "algorithmic_bytes": bytes_, "peak_source": peaks["src"],
-                        "instances_R": R_avg}
-            out["roofline"] = roof(b_bwd, prof["render_bwd"], "render_bwd_pair_kernel")
-            out["roofline_fwd"] = roof(b_fwd, prof["render_fwd"], "render_fwd_pair_kernel")
+            prof, R_avg, V_avg = stage_profile(step, wl, device, min(args.steps, 16))
+            out["roofline"], out["roofline_fwd"] = rooflines(prof, R_avg, W, H, args.workload)
             out["stage_ms"] = prof
+            out["scene"] = {"P": P, "V": V_avg, "R": R_avg, "R_over_P": R_avg / P}
         except Exception as ex:   # measurement must not take the headline down with it
             out["roofline_error"] = repr(ex)
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
             try:
                 out["cpu_baseline"], _ = cpu_baseline(wl, step)
             except Exception as ex:
                 out["cpu_baseline_error"] = repr(ex)
-    # ---- last leg: the data-parallel TRAINING iteration (row f3).  It is the only one that maps memory across ranks; it
-    # runs after everything else has been measured and under a watchdog, so a stuck rendezvous cannot take the line down
-    if wl.get("params") is not None:
-        import threading
+
+    side_steps = max(10, min(args.steps, 40))
+    gts = None
+    if wl.get("params") is not None and not args.quick:
+        if ours:
+            dstep = cb.CameraBatch(wl, device, mode="raster", mask="gather")
+            secs_g, _, _ = timed_loop(dstep, wl, device, args.steps, args.warmup, world, e2e=False)
+            out["dropin"] = {"value": world * args.steps / secs_g, "unit": UNIT,
+                             "note": "plain drop-in: Frosting's boolean gathers in torch (frosting_model.py:1578-1586) + our "
+                                     "rasterizer, no visibility_mask extension"}
+            del dstep
+        fstep = make_step(args.impl, wl, device, mode="frosting")
+        secs_f, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
+        out["frosting_step"] = {"value": world * args.steps / secs_f, "unit": UNIT,
+                                "note": "secondary: the same frame starting from Frosting's learnable parameters "
+                                        "(attribute construction, row a20, inside the step)"}
+        # ... and with the trainers' real loss, 0.8 L1 + 0.2 (1 - SSIM) against a ground-truth image (refine.py:407-409)
+        gtg = torch.Generator().manual_seed(99 + rank)
+        gts = [torch.rand(3, H, W, generator=gtg).to(device) for _ in wl["cams"]]
+        fstep = make_step(args.impl, wl, device, mode="frosting", loss="l1_dssim")
+        fstep.gt = gts
+        secs_t, _, _ = timed_loop(fstep, wl, device, args.steps, args.warmup, world, e2e=False)
+        out["frosting_train_step"] = {"value": world * args.steps / secs_t, "unit": UNIT,
+                                      "note": "secondary: parameters -> attributes -> mask -> rasterizer -> 0.8 L1 + 0.2 (1-SSIM) "
+                                              "-> backward (ours: fused loss kernel, row f2; reference: its torch loss)"}
+        del fstep
+        if ours and world == 1:
+            try:
+                out["prepass_ms"] = prepass_ms(wl, device)
+            except Exception as ex:
+                out["prepass_error"] = repr(ex)
+
+    # ---- the data-parallel TRAINING iteration (row f3).  It is the only leg that maps memory across ranks; it runs under
+    # a watchdog, so a stuck rendezvous cannot take the line down
+    if wl.get("params") is not None and not args.quick:
         lock, finished = threading.Lock(), [False]
 
         def bail():
@@ -600,7 +585,7 @@ def main():
         timer.daemon = True
         timer.start()
         try:
-            dstep = OursDPTrainStep(wl, device) if args.impl == "ours" else ReferenceDPTrainStep(wl, device)
+            dstep = OursDPTrain(wl, device) if ours else ReferenceDPTrain(wl, device)
             dstep.gt = gts
             secs_d, _, _ = timed_loop(dstep, wl, device, args.steps, args.warmup, world, e2e=False)
             out["dp_train_step"] = {
@@ -608,8 +593,13 @@ def main():
                 "note": "secondary: one camera per rank per iteration, loss as above, then gradient mean over the ranks + Adam "
                         "with the reference's groups (ours: ONE peer-memory reduce+Adam+publish kernel per rank, row f3; "
                         "reference: NCCL all-reduce of each .grad + torch.optim.Adam)"}
-            if args.impl == "ours":
+            if ours:
                 out["dp_train_step"]["transport"] = dstep.opt.slabs.transport
+                if hasattr(dstep.opt, "replica_check"):
+                    try:
+                        out["dp_check"] = dstep.opt.replica_check()
+                    except Exception as ex:
+                        out["dp_check"] = {"error": repr(ex)}
                 dstep.opt.close()
             del dstep
         except Exception as ex:
@@ -617,6 +607,19 @@ def main():
         with lock:
             finished[0] = True
         timer.cancel()
+
+    # ---- the other BASELINE configs, one GPU, shipped kernels (they are parity-test cases first: tests/test_bench_configs_gpu.py)
+    if world == 1 and args.workload == "c3" and not args.quick:
+        del step
+        wl.clear()
+        torch.cuda.empty_cache()
+        for name, rr in (("c2", RING_RADIUS), ("c5", RING_RADIUS), ("c3_ring10", 10.0)):
+            try:
+                out[name] = side_config("c3" if name == "c3_ring10" else name, args.impl, device, side_steps,
+                                        max(3, args.warmup // 2), local_rank, ring_radius=rr)
+            except Exception as ex:
+                out[name + "_error"] = repr(ex)
+
     if rank == 0:
         os.write(result_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

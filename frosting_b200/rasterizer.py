@@ -15,6 +15,8 @@ instead of boolean-gathering every attribute tensor (frosting_model.py:1578-1586
 """
 from typing import NamedTuple, Optional
 import ctypes as C
+import os
+import threading
 
 import torch
 import torch.nn as nn
@@ -38,11 +40,13 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-_last = {"num_rendered": 0}
 NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove it is output-neutral
+# FB200_EXACT_BINNING=1: always size the binning buffer from this frame's own instance count (two-phase forward with a
+# host wait, like the reference's blocking copy at rasterizer_impl.cu:280-281) instead of speculating from earlier frames
+EXACT_BINNING = os.environ.get("FB200_EXACT_BINNING", "0") == "1"
+_HEADROOM = 2.0           # speculative capacity = _HEADROOM x (largest count seen for this problem size) + 64 Ki
+_RING = 8                 # status mailboxes in flight per (thread, device)
 
-
-_pinned = {}
 _size_cache = {}
 
 
@@ -59,16 +63,87 @@ def _sizes(L, P, W, H):
     return v
 
 
-_capacity_hint = {}     # (device, P, W, H) -> binning capacity to pre-allocate
+class BinningOverflow(RuntimeError):
+    """A frame's tile-instance count exceeded the capacity its binning buffer was launched with.  Nothing was rendered
+    for that frame (the kernels see the overflow word and exit), its outputs are invalid; the capacity hint has been
+    raised, re-running the frame succeeds."""
 
 
-def _pinned_status(device):
-    # one pinned 32-byte mailbox per device: cudaHostAlloc per call would cost more than the frame
-    t = _pinned.get(device.index)
-    if t is None:
-        t = torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, pin_memory=True)
-        _pinned[device.index] = t
-    return t
+class _Pending:
+    __slots__ = ("slot", "event", "capacity", "key", "done", "num_rendered", "overflow", "reported")
+
+
+class _HostState:
+    """Host-side state of ONE host thread on ONE device: capacity hints, the ring of pinned status mailboxes and
+    the frames whose status words have not been looked at yet.  Per (thread, device), so one host thread per GPU --
+    or several threads on one GPU -- never share a mailbox (re-entrant, no globals across threads)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.hints = {}            # (P, W, H) -> capacity to launch the next frame of this size with
+        self.slots = [torch.empty((_lib.FB200_STATUS_WORDS,), dtype=torch.int32, pin_memory=True) for _ in range(_RING)]
+        self.events = [torch.cuda.Event() for _ in range(_RING)]
+        self.next = 0
+        self.pending = []          # oldest first
+        self.overflowed = []       # resolved, overflowed, not yet reported
+        self.last_num_rendered = 0
+
+    def mailbox(self):
+        """A free pinned mailbox; a frame still holding the next one is waited for first (it finished long ago)."""
+        i = self.next
+        self.next = (i + 1) % _RING
+        for p in list(self.pending):
+            if p.slot is self.slots[i]:
+                try:
+                    self.resolve(p)
+                except BinningOverflow:
+                    p.reported = False        # leave the report to the frame's own backward / the next poll
+                    self.overflowed.append(p)
+        return self.slots[i], self.events[i]
+
+    def resolve(self, p, wait=True):
+        """Read a frame's status words once its copy has landed; raises BinningOverflow (once) for an overflowed frame."""
+        if not p.done:
+            if not wait and not p.event.query():
+                return False
+            p.event.synchronize()
+            p.num_rendered = int(p.slot[_lib.ST_NUM_RENDERED])
+            p.overflow = bool(int(p.slot[_lib.ST_OVERFLOW])) or p.num_rendered > p.capacity or p.num_rendered < 0
+            p.done = True
+            if p in self.pending:
+                self.pending.remove(p)
+            self.last_num_rendered = p.num_rendered
+            want = int(max(p.num_rendered, 0) * _HEADROOM) + 65536
+            if want > self.hints.get(p.key, 0):
+                self.hints[p.key] = want
+        if p.overflow and not p.reported:
+            p.reported = True
+            raise BinningOverflow(
+                f"frosting_b200: a frame produced {p.num_rendered} tile instances but was launched with binning capacity "
+                f"{p.capacity} (speculated from earlier frames of this size); that frame's outputs are invalid. The "
+                "capacity has been raised -- re-run the frame, or set FB200_EXACT_BINNING=1 to size every frame exactly.")
+        return True
+
+    def poll(self):
+        """Look at every earlier frame whose status copy has completed (no waiting)."""
+        while self.overflowed:
+            self.resolve(self.overflowed.pop(0))
+        for p in list(self.pending):
+            if not self.resolve(p, wait=False):
+                break
+
+
+_tls = threading.local()
+
+
+def _host_state(device) -> _HostState:
+    d = getattr(_tls, "states", None)
+    if d is None:
+        d = _tls.states = {}
+    st = d.get(device.index)
+    if st is None:
+        st = d[device.index] = _HostState(device)
+    return st
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -84,18 +159,36 @@ def _f32c(t: torch.Tensor, device, name: str) -> torch.Tensor:
         raise TypeError(f"{name} must be float32, got {t.dtype}")
     if t.device != device:
         t = t.to(device)
-    return t if t.is_contiguous() else t.contiguous()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        # the kernels read rows with 128-bit loads; a contiguous VIEW at an odd storage offset is legal for the
+        # reference (scalar loads) and must be legal here: copy it to an aligned allocation
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
 
 
 class _Call:
     """Everything one forward needs again in backward (kept alive by the autograd ctx)."""
     __slots__ = ("prm", "inp", "ws", "tensors", "geom", "image", "binning", "status", "capacity",
-                 "num_rendered", "device", "extra")
+                 "_num_rendered", "device", "extra", "pending", "host")
+
+    @property
+    def num_rendered(self) -> int:
+        """R of this frame; for a speculatively launched frame this waits for its status copy (usually long done)."""
+        if self._num_rendered is None:
+            self.host.resolve(self.pending)
+            self._num_rendered = self.pending.num_rendered
+        return self._num_rendered
+
+    def check(self):
+        """Raise if this frame overflowed its binning capacity (called before its backward is launched)."""
+        if self.pending is not None:
+            self.host.resolve(self.pending)
 
 
-def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    rs: GaussianRasterizationSettings, visibility, extra_features=None, extra_bg=None):
-    L = _lib.lib()
+def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, visibility,
+             extra_features, extra_bg):
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:57-59
     if not means3D.is_cuda:
@@ -125,7 +218,6 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
     M = sh.size(1) if sh.numel() != 0 else 0   # rasterize_points.cu:84-87
 
     # row f4: extra feature channels blended in the same traversal
-    extra = None
     if extra_features is not None:
         extra_features = _f32c(extra_features, device, "extra_features")
         if extra_features.dim() != 2 or extra_features.size(0) != P or not (1 <= extra_features.size(1) <= 3):
@@ -144,6 +236,31 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
                  d_colors_precomp=_ptr(colors_precomp), d_opacities=_ptr(opacities), d_scales=_ptr(scales),
                  d_rotations=_ptr(rotations), d_cov3D_precomp=_ptr(cov3Ds_precomp),
                  d_viewmatrix=_ptr(view), d_projmatrix=_ptr(proj), d_campos=_ptr(campos), d_visibility=_ptr(vis))
+    tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, view, proj,
+               campos, vis, extra_features, extra_bg)
+    return device, P, W, H, prm, inp, tensors, extra_features, extra_bg
+
+
+def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                    rs: GaussianRasterizationSettings, visibility, extra_features=None, extra_bg=None,
+                    want_backward=False, exact=False, geometry_only=False):
+    """One forward through the C ABI.
+
+    Default: ONE-PHASE, no host wait.  `fb200_forward` is launched with a binning capacity speculated from earlier frames
+    of this problem size (2x the largest count seen); the frame's status words travel to a pinned mailbox behind the
+    kernels and are looked at lazily -- by a later call on this thread, or before this frame's backward.  An overflow
+    (never silently wrong: the kernels exit on the overflow word) raises BinningOverflow and the next frame of this
+    size is sized from the count that overflowed.  The FIRST frame of a problem size, `debug`, `exact=True` and
+    FB200_EXACT_BINNING=1 take the two-phase path: preprocess + tile scan, host reads the exact count (the reference
+    blocks at the same point, rasterizer_impl.cu:280-281), raster phase with an exactly sized buffer.
+    """
+    L = _lib.lib()
+    device, P, W, H, prm, inp, tensors, extra_features, extra_bg = _prepare(
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, visibility, extra_features,
+        extra_bg)
+    host = _host_state(device)
+    host.poll()
+    extra = None
 
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device)
@@ -161,50 +278,61 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
         slab = torch.empty((gb + ib + 128,), dtype=torch.uint8, device=device)   # one allocator call
         geom, image = slab[:gb], slab[gb:gb + ib]
         status = slab[gb + ib:gb + ib + 4 * _lib.FB200_STATUS_WORDS].view(torch.int32)
-        status_host = _pinned_status(device)
-
-        # Phase 1: preprocess + tile scan.  The exact instance count R comes back through a pinned
-        # mailbox; waiting for it covers ~0.1 ms of GPU work (the reference blocks at the same point,
-        # rasterizer_impl.cu:280-281).  Phase 2 is then launched with an exactly sized binning buffer and
-        # the caller's loss/backward launches queue up behind it while the GPU is busy.
         ws = Workspace(d_geom=geom.data_ptr(), geom_bytes=geom.numel(),
                        d_image=image.data_ptr(), image_bytes=image.numel(),
                        d_binning=None, binning_bytes=0, binning_capacity=0, d_status=status.data_ptr(),
-                       # a backward will follow: clear its accumulators while the host waits for R (below)
-                       acc_zeroed_by_forward=1 if torch.is_grad_enabled() else 0)
+                       # a backward will follow: its accumulators are cleared inside the forward's launch sequence
+                       acc_zeroed_by_forward=1 if want_backward else 0)
         rptr = C.c_void_p(radii.data_ptr()) if P > 0 else None
         sptr = C.c_void_p(stream.cuda_stream)
-        _lib.check(L.fb200_forward_geometry(C.byref(prm), C.byref(inp), C.byref(ws), rptr, sptr))
-        status_host.copy_(status, non_blocking=True)
-        # the binning buffer is allocated BEFORE the wait from the last count seen for this problem size, so that the
-        # host's critical path after the wait is one comparison and one library call
-        hint_key = (device.index, P, W, H)
-        capacity = _capacity_hint.get(hint_key, 0)
-        binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device) if capacity else None
-        stream.synchronize()
-        num_rendered = int(status_host[_lib.ST_NUM_RENDERED])
-        if num_rendered > capacity or binning is None:
+        key = (P, W, H)
+        hint = host.hints.get(key, 0)
+        mailbox, event = host.mailbox()
+        pending = None
+        if exact or geometry_only or EXACT_BINNING or rs.debug or hint == 0:
+            # two-phase: exact count through the mailbox, then the raster phase
+            _lib.check(L.fb200_forward_geometry(C.byref(prm), C.byref(inp), C.byref(ws), rptr, sptr))
+            mailbox.copy_(status, non_blocking=True)
+            stream.synchronize()
+            num_rendered = int(mailbox[_lib.ST_NUM_RENDERED])
             capacity = max(num_rendered, 1)
+            binning = None
+            if not geometry_only:
+                binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
+                ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
+                ws.h_status = mailbox.data_ptr()     # the host HAS this frame's status words: empty sort classes are skipped
+                _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
+                                                  C.c_void_p(out_color.data_ptr()), rptr, sptr))
+                ws.h_status = None
+            host.hints[key] = max(hint, int(num_rendered * _HEADROOM) + 65536)
+            host.last_num_rendered = num_rendered
+        else:
+            capacity = hint
             binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
-        _capacity_hint[hint_key] = max(int(num_rendered * 1.05) + 1024, 1)
-        ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
-        ws.h_status = status_host.data_ptr()      # the mailbox holds this frame's status words until the next forward
-        _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
-                                          C.c_void_p(out_color.data_ptr()), rptr, sptr))
-        _last["num_rendered"] = num_rendered
+            ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
+            _lib.check(L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws), C.c_void_p(out_color.data_ptr()),
+                                       rptr, sptr))
+            mailbox.copy_(status, non_blocking=True)
+            event.record(stream)
+            pending = _Pending()
+            pending.slot, pending.event, pending.capacity, pending.key = mailbox, event, capacity, key
+            pending.done, pending.num_rendered, pending.overflow, pending.reported = False, None, False, False
+            host.pending.append(pending)
+            num_rendered = None
 
     call = _Call()
     call.prm, call.inp, call.ws = prm, inp, ws
-    call.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, view, proj,
-                    campos, vis, extra_features, extra_bg)
+    call.tensors = tensors
     call.extra = extra
     call.geom, call.image, call.binning, call.status = geom, image, binning, status
-    call.capacity, call.num_rendered, call.device = capacity, num_rendered, device
+    call.capacity, call._num_rendered, call.device = capacity, num_rendered, device
+    call.pending, call.host = pending, host
     return out_color, radii, call, out_extra
 
 
 def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None):
     L = _lib.lib()
+    call.check()       # a speculatively launched forward that overflowed has no state to differentiate: raise
     prm = call.prm
     P, M = prm.P, prm.sh_coeffs
     device = call.device
@@ -251,9 +379,15 @@ def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None):
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dextra
 
 
-def last_num_rendered() -> int:
-    """R (tile instances) of the most recent forward in this process."""
-    return _last["num_rendered"]
+def last_num_rendered(device=None) -> int:
+    """R (tile instances) of the most recent forward of this host thread on `device` (default: current device).
+    Waits for that frame's status copy if it has not been looked at yet."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    host = _host_state(torch.device(device))
+    for p in list(host.pending):
+        host.resolve(p)
+    return host.last_num_rendered
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -262,17 +396,23 @@ def cpu_deep_copy_tuple(input_tuple):
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings, visibility_mask=None, extra_features=None, extra_background=None):
+    # autograd.Function.forward always runs with grad mode off: whether a backward can follow is decided HERE
+    want_backward = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad
+        for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra_features))
     out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                    cov3Ds_precomp, raster_settings, visibility_mask, extra_features, extra_background)
+                                    cov3Ds_precomp, raster_settings, visibility_mask, extra_features, extra_background,
+                                    want_backward)
     return out if extra_features is not None else out[:2]
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, visibility_mask=None, extra_features=None, extra_background=None):
+                raster_settings, visibility_mask=None, extra_features=None, extra_background=None,
+                want_backward=False):
         args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-                visibility_mask, extra_features, extra_background)
+                visibility_mask, extra_features, extra_background, want_backward)
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args[:7])   # copy before they can be corrupted
             try:
@@ -283,8 +423,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise ex
         else:
             color, radii, call, extra = _launch_forward(*args)
-        ctx.call = call
-        ctx.num_rendered = call.num_rendered
+        ctx.call = call          # call.num_rendered: the reference's ctx.num_rendered (__init__.py:96), resolved lazily
         ctx.raster_settings = raster_settings
         ctx.present = tuple(t.numel() != 0 for t in (sh, colors_precomp, scales, rotations, cov3Ds_precomp))
         ctx.save_for_backward(radii)
@@ -322,6 +461,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             None,
             None,
             grad_extra,
+            None,
             None,
         )
 
@@ -389,7 +529,7 @@ def forward_with_state(raster_settings, means3D, opacities, shs=None, colors_pre
         color, radii, call, _ = _launch_forward(
             means3D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
             e if scales is None else scales, e if rotations is None else rotations,
-            e if cov3D_precomp is None else cov3D_precomp, raster_settings, visibility_mask)
+            e if cov3D_precomp is None else cov3D_precomp, raster_settings, visibility_mask, exact=True)
     P, W, H = call.prm.P, call.prm.image_width, call.prm.image_height
     lay = Layout()
     _lib.check(_lib.lib().fb200_get_layout(P, W, H, call.capacity, C.byref(lay)))
@@ -414,3 +554,29 @@ def forward_with_state(raster_settings, means3D, opacities, shs=None, colors_pre
         keys=view(call.binning, lay.bin_keys, R * 8, torch.int64),
     )
     return st
+
+
+def geometry_state(raster_settings, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                   cov3D_precomp=None, visibility_mask=None):
+    """Geometry phase only (preprocess + tile scan, `fb200_forward_geometry`): radii, depth bits, tile rects, per-tile
+    counts and the instance count, without binning or blending -- the preprocess sweep of the parity tests."""
+    e = torch.Tensor([])
+    with torch.no_grad():
+        _, radii, call, _ = _launch_forward(
+            means3D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
+            e if scales is None else scales, e if rotations is None else rotations,
+            e if cov3D_precomp is None else cov3D_precomp, raster_settings, visibility_mask, geometry_only=True)
+    P, W, H = call.prm.P, call.prm.image_width, call.prm.image_height
+    lay = Layout()
+    _lib.check(_lib.lib().fb200_get_layout(P, W, H, 0, C.byref(lay)))
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+
+    def view(buf, off, nbytes, dtype):
+        base = (-buf.data_ptr()) % 128
+        return buf[base + off: base + off + nbytes].view(dtype)
+
+    return dict(radii=radii, num_rendered=call.num_rendered, call=call,
+                depth=view(call.geom, lay.geom_depth, P * 4, torch.float32),
+                rect=view(call.geom, lay.geom_rect, P * 8, torch.int32).view(P, 2),
+                rec=view(call.geom, lay.geom_rec, P * 48, torch.float32).view(P, 12),
+                tile_count=view(call.image, lay.img_tile_count, T * 4, torch.int32))

@@ -6,7 +6,8 @@ import pytest
 import torch
 
 import frosting_b200 as fb
-from frosting_b200 import scenes, sharding
+from frosting_b200 import scenes
+from frosting_b200 import camera_batch as sharding
 
 
 def test_settings_namedtuple_matches_reference_field_order():

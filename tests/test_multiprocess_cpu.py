@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from frosting_b200 import sharding
+from frosting_b200 import camera_batch as sharding
 
 
 def _free_port():
@@ -23,7 +23,13 @@ def _worker(rank, world, port, q):
     total = sharding.reduce_loss(local)
     t = torch.tensor([1.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)             # the max-over-ranks timing reduction of bench.py
-    q.put((rank, cams, float(local), float(total), float(t)))
+    # the per-frame loss reduction of CameraBatch.run: one asynchronous all-reduce per frame, collected every K frames
+    red = sharding.LossReducer()
+    for c in cams:
+        red.add(torch.tensor(float((c + 1) ** 2)))
+    per_frame = red.collect().tolist()
+    assert red.collect().numel() == 0
+    q.put((rank, cams, float(local), float(total), float(t), per_frame))
     dist.destroy_process_group()
 
 
@@ -43,3 +49,6 @@ def test_camera_sharding_and_loss_allreduce_world2():
     expect = float(sum((c + 1) ** 2 for c in range(16)))
     assert all(r[3] == expect for r in res) and res[0][2] + res[1][2] == expect
     assert all(r[4] == 2.0 for r in res)
+    # frame k of rank 0 is reduced with frame k of rank 1 (cameras k and 8 + k)
+    expect_frames = [float((k + 1) ** 2 + (8 + k + 1) ** 2) for k in range(8)]
+    assert all(r[5] == expect_frames for r in res)
