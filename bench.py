@@ -175,7 +175,7 @@ class OursDPTrain(cb.CameraBatch):
     def __init__(self, wl, device):
         import frosting_b200 as fb
         opt = fb.FrostingAdam.for_frosting(wl["params"])
-        super().__init__(wl, device, mode="frosting", mask="fused", loss="l1_dssim", optimizer=opt)
+        super().__init__(wl, device, mode="frosting", mask="lookup", loss="l1_dssim", optimizer=opt)
 
     def frame(self, i, rs, cot):
         loss = super().frame(i, rs, cot).reshape(1).clone()
@@ -503,7 +503,8 @@ def main():
             "gaussians": P, "image": f"{W}x{H}", "sh_degree": wl["D"], "cameras_per_gpu": cb.CAMS_PER_GPU,
             "parallelism": f"camera-batch x{world} (Gaussians replicated, NCCL all-reduce of the scalar loss, "
                            "asynchronous per frame)",
-            "frame": "occlusion mask + rasterizer forward + (color*G).sum() + backward to all attributes",
+            "frame": "occlusion culling (visible-face lookup inside preprocess) + rasterizer forward + (color*G).sum() + "
+                     "backward to all attributes",
             "l2": "inputs larger than L2: ~236 B x P of attributes read per frame, no flush needed",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -24,7 +24,7 @@ EXPORTED = [
     "fb200_adam_step", "fb200_peer_alloc", "fb200_peer_free", "fb200_peer_export", "fb200_peer_open", "fb200_peer_close",
 ]
 NUM_STAGES = 5
-ABI_VERSION = 2
+ABI_VERSION = 3
 STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
 
 
@@ -46,7 +46,8 @@ class Extra(C.Structure):
 class Inputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_background", "d_means3D", "d_shs", "d_colors_precomp", "d_opacities", "d_scales",
-        "d_rotations", "d_cov3D_precomp", "d_viewmatrix", "d_projmatrix", "d_campos", "d_visibility")]
+        "d_rotations", "d_cov3D_precomp", "d_viewmatrix", "d_projmatrix", "d_campos", "d_visibility",
+        "d_point_cells", "d_face_visible")] + [("n_cell_points", C.c_int64)]
 
 
 class Workspace(C.Structure):
@@ -71,7 +72,7 @@ class FrostingParams(C.Structure):
     _fields_ = [("P", C.c_int32), ("n_verts", C.c_int32), ("n_faces", C.c_int32), ("sh_rest", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("d_bary_logits", "d_cells", "d_faces", "d_inner_verts", "d_outer_verts",
                                           "d_opacity_logits", "d_log_scales", "d_quats", "d_sh_dc", "d_sh_rest",
-                                          "d_mask")]
+                                          "d_mask", "d_face_visible")]
 
 
 class FrostingGrads(C.Structure):

@@ -140,13 +140,15 @@ class CameraBatch:
 
     mode   "raster"    inputs are the rasterizer's own tensors (the a1-a19 path): mask -> forward -> loss -> backward
            "frosting"  the frame starts from Frosting's learnable parameters (rows a20 / f1)
-    mask   "fused"     the occlusion mask is consumed inside preprocess (`visibility_mask=`)
+    mask   "lookup"    occlusion culling looked up inside preprocess from the visible-face marks (`face_visibility=`): no
+                       mask tensor, no mask kernel (row f1)
+           "fused"     a per-Gaussian mask tensor consumed inside preprocess (`visibility_mask=`, row a19)
            "gather"    plain drop-in: Frosting's boolean gathers in torch (frosting_model.py:1578-1586) feed the rasterizer
     loss   "cot"       (color * G).sum() with a fixed random cotangent image (SURVEY.md 8d "frame")
            "l1_dssim"  0.8 L1 + 0.2 (1 - SSIM) against a ground-truth image (refine.py:407-409), fused kernel (row f2)
     """
 
-    def __init__(self, wl, device, mode="raster", mask="fused", loss="cot", optimizer=None):
+    def __init__(self, wl, device, mode="raster", mask="lookup", loss="cot", optimizer=None):
         import frosting_b200 as fb
         from . import scenes
         self.fb, self.scenes, self.wl, self.device = fb, scenes, wl, device
@@ -174,7 +176,9 @@ class CameraBatch:
     def frame(self, i, rs, cot):
         """forward + loss + backward of camera i of this rank; returns the detached scalar loss."""
         fb = self.fb
-        mask = self.render_mask(i)
+        lookup = self.mask_mode == "lookup" and self.wl["face_visible"] is not None
+        mask = None if lookup else self.render_mask(i)
+        fv = self.wl["face_visible"][i] if lookup else None
         if self.mode == "raster":
             L = self.leaves
             for v in L.values():
@@ -185,7 +189,7 @@ class CameraBatch:
                 for v in self.params.values():
                     v.grad = None
             a = fb.frosting_attributes_fused(self.params, self.wl["mesh"], mask,
-                                             grad_sink=self.opt.grads if self.opt is not None else None)
+                                             grad_sink=self.opt.grads if self.opt is not None else None, face_visible=fv)
         if mask is not None and self.mask_mode == "gather":
             keep = mask.bool()
             m3, op, sh, sc, ro = (a[k][keep] for k in ("means3D", "opacities", "shs", "scales", "rotations"))
@@ -196,7 +200,8 @@ class CameraBatch:
             means2D = torch.zeros(self.P, 3, device=self.device, requires_grad=True)
             color, radii = fb.GaussianRasterizer(rs)(
                 means3D=a["means3D"], means2D=means2D, opacities=a["opacities"], shs=a["shs"], scales=a["scales"],
-                rotations=a["rotations"], visibility_mask=mask)
+                rotations=a["rotations"], visibility_mask=mask,
+                face_visibility=(fv, self.wl["mesh"]["cells"]) if lookup else None)
         if self.loss_mode == "l1_dssim":
             loss = fb.l1_dssim_loss(color, self.gt[i], 0.2)
         else:

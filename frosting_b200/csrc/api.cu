@@ -56,6 +56,14 @@ int validate(const fb200_params* prm, const fb200_inputs* in, const fb200_worksp
         if (has_sh && (prm->sh_coeffs <= 0 || prm->sh_degree < 0 || prm->sh_degree > 3 ||
                        (prm->sh_degree + 1) * (prm->sh_degree + 1) > prm->sh_coeffs))
             return fail(FB200_EINVAL, "sh_degree / sh_coeffs inconsistent%s");
+        // rows read with 128-bit loads (header: Alignment)
+        if ((in->d_rotations && (reinterpret_cast<uintptr_t>(in->d_rotations) & 15)) ||
+            (has_sh && (prm->sh_coeffs * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(in->d_shs) & 15)))
+            return fail(FB200_EINVAL, "rotations / SH rows must be 16-byte aligned%s");
+        if ((in->d_point_cells == nullptr) != (in->d_face_visible == nullptr))
+            return fail(FB200_EINVAL, "give both d_point_cells and d_face_visible or neither%s");
+        if (in->d_point_cells && (in->n_cell_points < 0 || in->n_cell_points > prm->P))
+            return fail(FB200_EINVAL, "n_cell_points must be within [0, P]%s");
     }
     if (!in->d_background || !in->d_viewmatrix || !in->d_projmatrix || !in->d_campos)
         return fail(FB200_EINVAL, "camera tensors missing%s");
@@ -280,6 +288,9 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
                        (!in->d_cov3D_precomp && (!grads->d_dL_dscales || !grads->d_dL_drotations)) ||
                        (in->d_shs && prm->sh_coeffs > 0 && !grads->d_dL_dsh)))
         return fail(FB200_EINVAL, "gradient output pointers missing%s");
+    if ((grads->d_dL_drotations && (reinterpret_cast<uintptr_t>(grads->d_dL_drotations) & 15)) ||
+        (grads->d_dL_dsh && (prm->sh_coeffs * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(grads->d_dL_dsh) & 15)))
+        return fail(FB200_EINVAL, "dL/drotations / dL/dsh rows must be 16-byte aligned%s");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool debug = (prm->debug & 1) != 0;
     if (prm->P == 0) return FB200_OK;

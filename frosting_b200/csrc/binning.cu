@@ -128,9 +128,11 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     atomicMax(&s_max, lmax);
     __syncthreads();
     if (tid == 1023) {
-        status[FB200_ST_NUM_RENDERED] = (int32_t)run;
-        status[FB200_ST_OVERFLOW] = ((long long)run > capacity) ? 1 : 0;
+        // the instance count is reported as a non-negative int32: anything beyond that is an overflow whatever the capacity
+        status[FB200_ST_NUM_RENDERED] = run > 0x7fffffffu ? 0x7fffffff : (int32_t)run;
+        status[FB200_ST_OVERFLOW] = ((long long)run > capacity || run > 0x7fffffffu) ? 1 : 0;
         status[FB200_ST_MAX_TILE] = (int32_t)s_max;
+        status[FB200_ST_NUM_VISIBLE] = (int32_t)counters[3];   // counted by preprocess (Gaussians with radii > 0)
     }
     if (tid == 0) {
         counters[4] = (uint32_t)cls_total[0];            // tiny
@@ -504,7 +506,8 @@ cudaError_t launch_tile_scan(const FwdArgs& a, cudaStream_t s) {
 
 // set the overflow word for a raster phase launched with its own capacity
 __global__ void check_capacity_kernel(long long capacity, int32_t* __restrict__ status) {
-    status[FB200_ST_OVERFLOW] = ((long long)status[FB200_ST_NUM_RENDERED] > capacity) ? 1 : 0;
+    const int32_t r = status[FB200_ST_NUM_RENDERED];
+    status[FB200_ST_OVERFLOW] = ((long long)r > capacity || r == 0x7fffffff) ? 1 : 0;
 }
 
 // The tiny-list and small-list sorts are independent and each ends in a long tail (a few long lists on a few SMs);

@@ -57,7 +57,8 @@ frosting_attr_fwd_kernel(AttrArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g0 = idx - lane;
     const bool in_range = idx < P;
-    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0);
+    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0) &&
+                      !(a.p.d_face_visible != nullptr && a.p.d_face_visible[a.p.d_cells[idx]] == 0);
     const unsigned live_mask = __ballot_sync(full, live);
     if (live_mask == 0) return;
     // stage the warp's rest block when the warp is full and at least half of its rows are needed
@@ -126,7 +127,8 @@ frosting_attr_bwd_kernel(AttrBwdArgs a) {
     const int g0 = idx - lane;
     const bool full_warp = g0 + 31 < P;
     const bool in_range = idx < P;
-    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0);
+    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0) &&
+                      !(a.p.d_face_visible != nullptr && a.p.d_face_visible[a.p.d_cells[idx]] == 0);
     const unsigned live_mask = __ballot_sync(full, live);
     const size_t i = (size_t)(in_range ? idx : 0);
     float* srow = stage[warp];

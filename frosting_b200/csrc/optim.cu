@@ -70,6 +70,7 @@ adam_shard_kernel(const fb200_adam_args a) {
 #pragma unroll
         for (int k = 1; k < FB200_ADAM_MAX_GROUPS; ++k)
             if (k < a.n_groups && e >= a.group_start[k]) lr = a.lr[k];
+        if (lr < 0.f) continue;        // group without a gradient this step: untouched, like a torch parameter with .grad None
         const float step = lr / a.bias_correction1;
 
         const int64_t li = i - v_lo;
@@ -120,6 +121,7 @@ adam_shard_mc_kernel(const fb200_adam_args a) {
 #pragma unroll
         for (int k = 1; k < FB200_ADAM_MAX_GROUPS; ++k)
             if (k < a.n_groups && e >= a.group_start[k]) lr = a.lr[k];
+        if (lr < 0.f) continue;
         const float step = lr / a.bias_correction1;
         const int64_t li = i - v_lo;
         float4 m = mom1[li], v = mom2[li];

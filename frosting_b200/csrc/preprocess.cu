@@ -213,8 +213,9 @@ preprocess_fwd_kernel(FwdArgs a) {
     __syncthreads();
 
     const int P = a.prm.P;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = tid < P;          // no early exit: the tile counting at the end is warp-cooperative
+    const int idx = valid ? tid : P - 1;
 
     const float* __restrict__ v = cam.view;
     const float* __restrict__ m = cam.proj;
@@ -225,12 +226,16 @@ preprocess_fwd_kernel(FwdArgs a) {
 
     // in_frustum: keep iff !(p_view.z <= 0.2f)
     const float depth = affine_row(v, 2, px, py, pz);
-    bool keep = !(depth <= 0.2f);
-    if (!keep && a.prm.prefiltered) {
+    bool keep = valid && !(depth <= 0.2f);
+    if (valid && !keep && a.prm.prefiltered) {
         printf("Point is filtered although prefiltered is set. This shouldn't happen!");
         __trap();
     }
     if (a.in.d_visibility != nullptr && a.in.d_visibility[idx] == 0) keep = false;
+    // occlusion culling without a mask tensor: render_mask = face_visible[_point_cell_indices] for the mesh-bound
+    // Gaussians, True for the trailing background ones (frosting_model.py:1564-1576), looked up in place
+    if (a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points &&
+        a.in.d_face_visible[a.in.d_point_cells[idx]] == 0) keep = false;
     if (keep && a.in.d_shs != nullptr) {
         // the SH row (192 B at degree 3) is consumed last, after a chain of dependent loads; start it moving now
         const char* row = reinterpret_cast<const char*>(a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3);
@@ -344,16 +349,60 @@ preprocess_fwd_kernel(FwdArgs a) {
                 a.rec[idx] = r;
                 a.depth[idx] = depth;
                 a.clamped[idx] = clamp_bits;
-
-                // per-tile instance counts
-                for (uint32_t ty = miny; ty < maxy; ++ty)
-                    for (uint32_t tx = minx; tx < maxx; ++tx)
-                        atomicAdd(a.tile_count + ty * gx + tx, 1u);
             }
         }
     }
-    a.radii[idx] = radius;
-    a.rect[idx] = rect;
+    if (valid) {
+        a.radii[idx] = radius;
+        a.rect[idx] = rect;
+    }
+
+    // ---- per-tile instance counts, warp-balanced ----
+    // The reference's duplicateWithKeys walks each splat's tile rectangle in a serial per-thread double loop
+    // (rasterizer_impl.cu:98-108) and so did round 1's counting here: one 12x12-tile splat kept its warp busy for 144
+    // dependent iterations (C5: preprocess 0.77 ms).  Same expansion as scatter_kernel (binning.cu): the warp scans its
+    // 32 rectangle sizes and walks the concatenated instance list 32 instances per step.
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t minx = rect.x & 0xffffu, miny = rect.x >> 16;
+    const uint32_t w = (rect.y & 0xffffu) - minx;
+    const uint32_t cnt = w * ((rect.y >> 16) - miny);          // 0 unless the Gaussian is rendered
+    const unsigned vis = __ballot_sync(full, cnt != 0);
+    if (vis == 0) return;
+    if (lane == 0) atomicAdd(a.counters + 3, (uint32_t)__popc(vis));      // FB200_ST_NUM_VISIBLE
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = __shfl_sync(full, incl, 31);
+    const float rw = w ? __frcp_rn((float)w) : 0.f;
+    const uint32_t gxw = (uint32_t)a.tiles_x;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t item = base + lane;
+        int pos = 0;                      // owner = number of lanes whose inclusive count is <= item
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t t = __shfl_sync(full, incl, pos + step - 1);
+            if (t <= item) pos += step;
+        }
+        const int owner = min(pos, 31);
+        const uint32_t o_excl = __shfl_sync(full, excl, owner);
+        const uint32_t o_min = __shfl_sync(full, rect.x, owner);
+        const uint32_t o_w = __shfl_sync(full, w, owner);
+        const float o_rw = __shfl_sync(full, rw, owner);
+        if (item < total) {
+            const uint32_t k = item - o_excl;
+            // k / o_w through the reciprocal (both < 2^24), corrected by at most one either way
+            uint32_t q = __float2uint_rz(__fmul_rn((float)k, o_rw));
+            int rem = (int)k - (int)(q * o_w);
+            if (rem < 0) { --q; rem += (int)o_w; } else if (rem >= (int)o_w) { ++q; rem -= (int)o_w; }
+            const uint32_t ty = (o_min >> 16) + q, tx = (o_min & 0xffffu) + (uint32_t)rem;
+            atomicAdd(a.tile_count + ty * gxw + tx, 1u);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -370,7 +419,10 @@ mark_visible_kernel(int P, const float* __restrict__ means, const float* __restr
 
 cudaError_t launch_preprocess_fwd(const FwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
-    cudaError_t e = cudaMemsetAsync(a.tile_count, 0, sizeof(uint32_t) * T, s);
+    // the per-tile counts and the counter words behind them (adjacent in the image workspace) in one memset
+    const size_t span = (size_t)(reinterpret_cast<const char*>(a.counters) - reinterpret_cast<const char*>(a.tile_count)) + 64;
+    (void)T;
+    cudaError_t e = cudaMemsetAsync(a.tile_count, 0, span, s);
     if (e != cudaSuccess) return e;
     if (a.prm.P > 0) {
         const int blocks = (a.prm.P + 255) / 256;

@@ -331,6 +331,248 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     }
 }
 
+
+// ---- v4: transposed blocks -- lane = Gaussian for the per-pair math, lane = pixel for the recurrences --------------------
+// The pair kernel above keeps lane = pixel throughout, so every Gaussian's 9 partial gradients must be summed over the
+// warp: 36 % of its pair loop is the transposing butterfly (20 SHFL + 36 FSEL per two Gaussians,
+// profiles/r01_pair_loop_sass_budget.json).  Here the hits of a warp's 8x4 sub-tile are processed in blocks of 16
+// Gaussians and the work is split by what each part needs:
+//   phase 1  lane = (Gaussian g, pixel half h): the lane evaluates ITS Gaussian at its 16 pixels, two pixels at a time on
+//            packed fp32 -- same op order as the forward (power / libdevice exp / alpha tests, bit-identical decisions) --
+//            and leaves three values per (Gaussian, pixel) in a padded shared-memory matrix: the masked opacity*G, the
+//            1/(1-alpha) of the pair and alpha * (colour . dL/dpixel);
+//   phase 2  lane = pixel: the only sequential part, the back-to-front recurrences, walks the 16 Gaussians of the block
+//            for the lane's own pixel -- T <- T/(1-alpha), E <- E + alpha T (c . dL/dpix) -- two loads, four flops and two
+//            stores per pair; the per-pixel state (T, E) lives in registers across blocks.  It leaves T_g and
+//            U = (K - E_g)/(1-alpha) in place of the inputs, so that dL/dalpha = T_g (c . dL/dpix) + U
+//            (backward.cu:509-534 with accum_rec kept un-normalised: T_g * accum_rec = E_g / (1 - alpha_g));
+//   phase 3  lane = (g, h) again: gradient algebra for its Gaussian, accumulated over its 16 pixels IN REGISTERS as five
+//            image moments of S = dL/dG * G (sum S dx, S dy, S dx^2, S dx dy, S dy^2), sum S / opacity-side and the three
+//            colour sums; no cross-lane reduction except one xor-16 add per block.  9 red.global.add per Gaussian, as before.
+// No shuffle and no select in the inner loops; the matrix rows are padded to 34 floats so that the 64-bit row accesses of
+// phases 1/3 (lane stride = one row) and the 32-bit column accesses of phase 2 (lane stride = one word) are both
+// bank-conflict free.
+constexpr int kBlk = 16;            // Gaussians per block
+constexpr int kRow = 34;            // padded row length (floats) of the [kBlk][32 pixels] matrices
+constexpr int kQ = 64;              // hit queue capacity (>= kBlk - 1 + 32), power of two
+
+struct __align__(16) BwdWarpSmem {
+    float m0[kBlk * kRow];          // masked opacity * G                       (phase 1 -> phase 3)
+    float m1[kBlk * kRow];          // 1 / (1 - alpha)  -> T_g                  (phase 1 -> 2 -> 3)
+    float m2[kBlk * kRow];          // alpha * (c . dL/dpix)  -> U              (phase 1 -> 2 -> 3)
+    float dp0[32], dp1[32], dp2[32], K[32];     // per pixel: dL/dpixel, K = -T_final * (bg . dL/dpixel)
+    uint32_t last[32];                          // per pixel: n_contrib
+    float qx[kQ], qy[kQ], qA[kQ], qB[kQ], qC[kQ], qop[kQ], qr[kQ], qg[kQ], qb[kQ];   // hit queue (circular, SoA)
+    uint32_t qid[kQ], qpos[kQ];
+};
+
+template <int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, 20 / kWarps)
+render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                      const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
+                      const float* __restrict__ bg, const float* __restrict__ final_T,
+                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
+                      float* __restrict__ acc, const int32_t* __restrict__ status) {
+    __shared__ BwdWarpSmem smem[kWarps];
+    if (status[FB200_ST_OVERFLOW]) return;
+
+    const unsigned full = 0xffffffffu;
+    constexpr int kSplit = kWarpsPerTile / kWarps;
+    const int tile = blockIdx.x / kSplit;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int wslot = threadIdx.x >> 5;
+    const int warp = (blockIdx.x % kSplit) * kWarps + wslot;      // sub-tile index inside the tile
+    int lane;
+    unsigned lt_mask;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    BwdWarpSmem& sm = smem[wslot];
+    const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
+    const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
+    const float lox = (float)sub_x0, hix = (float)(sub_x0 + kSubW - 1);
+    const float loy = (float)sub_y0, hiy = (float)(sub_y0 + kSubH - 1);
+    const uint2 range = ranges[tile];
+
+    // ---- lane = pixel: the lane's own pixel, its recurrence state and its row of the per-pixel constants ----
+    float T, E = 0.f, Kp;
+    int n;
+    {
+        const int pix_x = sub_x0 + (lane & 7), pix_y = sub_y0 + (lane >> 3);
+        const bool inside = pix_x < W && pix_y < H;
+        const size_t pix_id = (size_t)pix_y * W + pix_x;
+        const size_t HW = (size_t)H * W;
+        const float T_final = inside ? final_T[pix_id] : 0.f;
+        const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+        float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+        if (inside) {
+            dp0 = dL_dpix[pix_id];
+            dp1 = dL_dpix[HW + pix_id];
+            dp2 = dL_dpix[2 * HW + pix_id];
+        }
+        Kp = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
+        T = T_final;
+        sm.dp0[lane] = dp0; sm.dp1[lane] = dp1; sm.dp2[lane] = dp2; sm.K[lane] = Kp; sm.last[lane] = last_contributor;
+        n = (int)__reduce_max_sync(full, last_contributor);
+    }
+    if (n == 0) return;
+    __syncwarp();
+
+    // ---- lane = (Gaussian g, pixel half h): rows 2h, 2h+1 of the 8x4 sub-tile ----
+    const int g = lane & (kBlk - 1), h = lane >> 4;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const float px0 = (float)sub_x0;
+    const float py0 = (float)(sub_y0 + 2 * h);
+    float* const row0 = sm.m0 + g * kRow + 16 * h;
+    float* const row1 = sm.m1 + g * kRow + 16 * h;
+    float* const row2 = sm.m2 + g * kRow + 16 * h;
+    const float* const pdp0 = sm.dp0 + 16 * h;
+    const float* const pdp1 = sm.dp1 + 16 * h;
+    const float* const pdp2 = sm.dp2 + 16 * h;
+    const uint32_t* const plast = sm.last + 16 * h;
+
+    auto process_block = [&](int head, int cnt) {
+        const bool valid = g < cnt;
+        const int slot = (head + g) & (kQ - 1);
+        const float X = sm.qx[slot], Y = sm.qy[slot], A = sm.qA[slot], B = sm.qB[slot], Cc = sm.qC[slot];
+        const float op = valid ? sm.qop[slot] : 0.f;
+        const float cr = valid ? sm.qr[slot] : 0.f, cg = valid ? sm.qg[slot] : 0.f, cb = valid ? sm.qb[slot] : 0.f;
+        const uint32_t pos = valid ? sm.qpos[slot] : 0xffffffffu;
+        const uint32_t gid = sm.qid[slot];
+        // ---- phase 1: alpha of (Gaussian g) x (16 pixels), the forward's op order ----
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float dy = fadd(Y, -(py0 + (float)r));
+            const float dyC = fmul(dy, fmul(dy, Cc));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = 8 * r + 2 * c;                                   // pixel pair (k, k+1) of this half
+                const P2 dx = add2(bc(X), p2(-(px0 + (float)(2 * c)), -(px0 + (float)(2 * c + 1))));
+                const P2 q = fma2(dx, mul2(dx, bc(A)), bc(dyC));
+                const P2 u = mul2(bc(dy), mul2(dx, bc(B)));
+                const P2 power = fma2(q, bc(-0.5f), neg2(u));
+                const P2 og = mul2(bc(op), exp_pair(power));
+                const uint2 lastp = *reinterpret_cast<const uint2*>(plast + k);
+                // contributes iff the forward blended it: before the pixel's last contributor, power <= 0, alpha >= 1/255
+                // (min(0.99, og) < 1/255  <=>  og < 1/255)
+                const bool a0 = (pos < lastp.x) && !(power.x > 0.0f) && !(og.x < 1.0f / 255.0f);
+                const bool a1 = (pos < lastp.y) && !(power.y > 0.0f) && !(og.y < 1.0f / 255.0f);
+                const P2 ogm = p2(a0 ? og.x : 0.f, a1 ? og.y : 0.f);
+                const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
+                const P2 om = add2(bc(1.0f), neg2(am));                        // 1 - alpha in [0.01, 1]
+                P2 inv;
+                {
+                    float i0, i1;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(om.x));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(om.y));
+                    const P2 rr = p2(i0, i1);
+                    inv = fma2(rr, fma2(neg2(om), rr, bc(1.0f)), rr);          // one Newton step
+                }
+                const P2 cd = fma2(ldp(pdp0, k), bc(cr), fma2(ldp(pdp1, k), bc(cg), mul2(ldp(pdp2, k), bc(cb))));
+                *reinterpret_cast<float2*>(row0 + k) = ogm;
+                *reinterpret_cast<float2*>(row1 + k) = inv;
+                *reinterpret_cast<float2*>(row2 + k) = mul2(am, cd);
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: lane = pixel, back-to-front recurrences over the block's Gaussians ----
+        {
+            float* c1 = sm.m1 + lane;
+            float* c2 = sm.m2 + lane;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const float inv = c1[i * kRow], bb = c2[i * kRow];
+                const float Tg = T * inv;                      // transmittance in front of Gaussian i at this pixel
+                c1[i * kRow] = Tg;
+                c2[i * kRow] = (Kp - E) * inv;                 // U: everything behind it (and the background) seen through it
+                E = fmaf(bb, Tg, E);
+                T = Tg;
+            }
+        }
+        __syncwarp();
+        // ---- phase 3: gradient sums of Gaussian g over its 16 pixels ----
+        const float rop = op > 0.f ? __frcp_rn(op) : 0.f;
+        P2 sR = bc(0.f), sG = bc(0.f), sB = bc(0.f), sO = bc(0.f);
+        P2 M10 = bc(0.f), M01 = bc(0.f), M20 = bc(0.f), M11 = bc(0.f), M02 = bc(0.f);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float dy = fadd(Y, -(py0 + (float)r));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = 8 * r + 2 * c;
+                const P2 dx = add2(bc(X), p2(-(px0 + (float)(2 * c)), -(px0 + (float)(2 * c + 1))));
+                const P2 ogm = ldp(row0, k), Tg = ldp(row1, k), U = ldp(row2, k);
+                const P2 d0 = ldp(pdp0, k), d1 = ldp(pdp1, k), d2 = ldp(pdp2, k);
+                const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
+                const P2 Gm = mul2(ogm, bc(rop));                               // G (0 where the pair does not contribute)
+                const P2 cd = fma2(d0, bc(cr), fma2(d1, bc(cg), mul2(d2, bc(cb))));
+                const P2 dch = mul2(am, Tg);                                   // d(pixel channel)/d(colour)
+                sR = fma2(dch, d0, sR); sG = fma2(dch, d1, sG); sB = fma2(dch, d2, sB);
+                const P2 dLa = fma2(Tg, cd, U);                                // dL/dalpha
+                const P2 S = mul2(dLa, Gm);                                    // dL/dopacity contribution
+                sO = add2(sO, S);
+                const P2 SG = mul2(S, bc(op));                                 // dL/dG * G
+                const P2 sx = mul2(SG, dx), sy = mul2(SG, bc(dy));
+                M10 = add2(M10, sx); M01 = add2(M01, sy);
+                M20 = fma2(sx, dx, M20); M11 = fma2(sx, bc(dy), M11); M02 = fma2(sy, bc(dy), M02);
+            }
+        }
+        float v[9] = {M10.x + M10.y, M01.x + M01.y, M20.x + M20.y, M11.x + M11.y, M02.x + M02.y,
+                      sO.x + sO.y, sR.x + sR.y, sG.x + sG.y, sB.x + sB.y};
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] += __shfl_xor_sync(full, v[i], 16);
+        if (h == 0 && valid) {
+            float* a = acc + (size_t)gid * 12;
+            // dG/ddelx = -G (dx A + dy B), dG/ddely = -G (dy C + dx B)   (backward.cu:536-546)
+            atomicAdd(a + 0, -ddelx_dx * fmaf(A, v[0], B * v[1]));
+            atomicAdd(a + 1, -ddely_dy * fmaf(Cc, v[1], B * v[0]));
+            atomicAdd(a + 2, -0.5f * v[2]);
+            atomicAdd(a + 3, -0.5f * v[3]);
+            atomicAdd(a + 4, -0.5f * v[4]);
+            atomicAdd(a + 5, v[5]);
+            atomicAdd(a + 6, v[6]);
+            atomicAdd(a + 7, v[7]);
+            atomicAdd(a + 8, v[8]);
+        }
+        __syncwarp();      // the matrices and the queue slots are rewritten next
+    };
+
+    // ---- walk the tile list back to front from the sub-tile's deepest last contributor, 32 instances per step ----
+    int head = 0, tail = 0;
+    uint32_t id_cur = 0, id_next = 0;
+    float4 r0, r1, r2;
+    r0 = r1 = r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < n) {
+        id_cur = point_list[range.x + (n - 1 - lane)];
+        const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
+        r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+    }
+    if (32 + lane < n) id_next = point_list[range.x + (n - 1 - 32 - lane)];
+    for (int base = 0; base < n; base += 32) {
+        const bool hit = (base + lane < n) && overlaps(lox, hix, r0.x, r2.y) && overlaps(loy, hiy, r0.y, r2.z);
+        const uint32_t bits = __ballot_sync(full, hit);
+        if (hit) {
+            const int slot = (tail + __popc(bits & lt_mask)) & (kQ - 1);
+            sm.qx[slot] = r0.x; sm.qy[slot] = r0.y; sm.qA[slot] = r0.z; sm.qB[slot] = r0.w;
+            sm.qC[slot] = r1.x; sm.qop[slot] = r1.y; sm.qr[slot] = r1.z; sm.qg[slot] = r1.w; sm.qb[slot] = r2.x;
+            sm.qid[slot] = id_cur;
+            sm.qpos[slot] = (uint32_t)(n - 1 - base - lane);
+        }
+        tail += __popc(bits);
+        id_cur = id_next;
+        if (base + 32 + lane < n) {
+            const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
+            r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+        }
+        if (base + 64 + lane < n) id_next = point_list[range.x + (n - 1 - base - 64 - lane)];
+        __syncwarp();
+        while (tail - head >= kBlk) {
+            process_block(head, kBlk);
+            head += kBlk;
+        }
+    }
+    if (tail > head) process_block(head, tail - head);
+}
+
 }  // namespace
 
 cudaError_t launch_render_bwd_clear(const BwdArgs& a, cudaStream_t s) {
@@ -346,10 +588,14 @@ cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
         render_bwd_pair_kernel<true, kWarps><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
             a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
-    else
+    else if (a.prm.debug & 4)       // A/B switch: the round-1 pair kernel (lane = pixel + butterfly)
         render_bwd_pair_kernel<false, kWarps><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
             a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+    else
+        render_bwd_t16_kernel<kWarps><<<grid, 32 * kWarps, 0, s>>>(
+            a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
+            a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status);
     return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ def _p(t):
 class _FrostingAttributes(torch.autograd.Function):
     @staticmethod
     def forward(ctx, bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, mask,
-                sink=None):
+                sink=None, face_visible=None):
         if not bary_logits.is_cuda:
             raise RuntimeError("frosting_b200 runs on CUDA tensors only (no CPU fallback)")
         dev = bary_logits.device
@@ -32,14 +32,15 @@ class _FrostingAttributes(torch.autograd.Function):
         cells = cells.to(device=dev, dtype=torch.int64).contiguous()
         faces = faces.to(device=dev, dtype=torch.int32).contiguous()
         m = None if mask is None else mask.to(device=dev, dtype=torch.uint8).contiguous()
+        fv = None if face_visible is None else face_visible.to(device=dev, dtype=torch.uint8).contiguous()
         P, R = bary_logits.shape[0], sh_rest.shape[1]
         fp = FrostingParams(P=P, n_verts=inner.shape[0], n_faces=faces.shape[0], sh_rest=R,
                             d_bary_logits=_p(bary_logits), d_cells=_p(cells), d_faces=_p(faces),
                             d_inner_verts=_p(inner), d_outer_verts=_p(outer), d_opacity_logits=_p(opacity_logits),
                             d_log_scales=_p(log_scales), d_quats=_p(quats), d_sh_dc=_p(sh_dc), d_sh_rest=_p(sh_rest),
-                            d_mask=_p(m))
+                            d_mask=_p(m), d_face_visible=_p(fv))
         o = dict(dtype=torch.float32, device=dev)
-        alloc = torch.empty if m is None else torch.zeros    # masked rows stay finite for downstream torch code
+        alloc = torch.empty if (m is None and fv is None) else torch.zeros    # masked rows stay finite for downstream torch code
         means3D, opac = alloc((P, 3), **o), alloc((P, 1), **o)
         scales, rots, shs = alloc((P, 3), **o), alloc((P, 4), **o), alloc((P, R + 1, 3), **o)
         with torch.cuda.device(dev):
@@ -48,13 +49,13 @@ class _FrostingAttributes(torch.autograd.Function):
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         ctx.fp = fp
         ctx.sink = sink
-        ctx.keep = (bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, m)
+        ctx.keep = (bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, m, fv)
         ctx.vert_grad = inner.requires_grad or outer.requires_grad
         return means3D, opac, scales, rots, shs
 
     @staticmethod
     def backward(ctx, g_means3D, g_opac, g_scales, g_rots, g_shs):
-        bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, m = ctx.keep
+        bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer, cells, faces, m, fv = ctx.keep
         dev = bary_logits.device
         P, R = bary_logits.shape[0], sh_rest.shape[1]
         o = dict(dtype=torch.float32, device=dev)
@@ -64,6 +65,8 @@ class _FrostingAttributes(torch.autograd.Function):
         if ctx.sink is not None:
             # gradients go straight into the optimizer's gradient slab (frosting_b200/optim.py); autograd gets None
             k = ctx.sink
+            if hasattr(k, "mark"):
+                k.mark(("bary_logits", "opacity_logits", "log_scales", "quats", "sh_dc", "sh_rest"))
             d_bary, d_op, d_ls = k["bary_logits"], k["opacity_logits"], k["log_scales"]
             d_q, d_dc, d_rest = k["quats"], k["sh_dc"], k["sh_rest"]
             for t, ref in ((d_bary, bary_logits), (d_op, opacity_logits), (d_ls, log_scales), (d_q, quats),
@@ -83,15 +86,16 @@ class _FrostingAttributes(torch.autograd.Function):
                 C.byref(ctx.fp), _p(g_means3D), _p(g_opac), _p(g_scales), _p(g_rots), _p(g_shs), C.byref(grads),
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         if ctx.sink is not None:
-            return (None, None, None, None, None, None, d_in, d_out, None, None, None, None)
-        return (d_bary, d_op.view_as(opacity_logits), d_ls, d_q, d_dc, d_rest, d_in, d_out, None, None, None, None)
+            return (None, None, None, None, None, None, d_in, d_out, None, None, None, None, None)
+        return (d_bary, d_op.view_as(opacity_logits), d_ls, d_q, d_dc, d_rest, d_in, d_out, None, None, None, None, None)
 
 
-def frosting_attributes_fused(params, mesh, mask=None, grad_sink=None):
+def frosting_attributes_fused(params, mesh, mask=None, grad_sink=None, face_visible=None):
     """params / mesh: the dicts of `scenes.frosting_layer` (bary_logits, opacity_logits, log_scales, quats, sh_dc,
     sh_rest | inner, outer, cells, faces).  Returns the rasterizer inputs.  `grad_sink` (dict with the parameter
-    names): the backward writes the parameter gradients there (overwriting) instead of returning them to autograd."""
+    names): the backward writes the parameter gradients there (overwriting) instead of returning them to autograd.
+    `face_visible` [F]: cull by face_visible[cells[i]] inside the kernels (the mask without a mask tensor)."""
     means3D, opac, scales, rots, shs = _FrostingAttributes.apply(
         params["bary_logits"], params["opacity_logits"], params["log_scales"], params["quats"], params["sh_dc"],
-        params["sh_rest"], mesh["inner"], mesh["outer"], mesh["cells"], mesh["faces"], mask, grad_sink)
+        params["sh_rest"], mesh["inner"], mesh["outer"], mesh["cells"], mesh["faces"], mask, grad_sink, face_visible)
     return dict(means3D=means3D, opacities=opac, scales=scales, rotations=rots, shs=shs)

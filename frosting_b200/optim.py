@@ -102,6 +102,28 @@ def _view(ptr, n, device):
     return torch.as_tensor(_DevicePointer(ptr, n), device=device)
 
 
+class GradSink(dict):
+    """name -> view into the gradient slab, plus the book-keeping torch keeps in `.grad is None`: which groups have
+    received a gradient since the last step / zero_grad.  Producers OVERWRITE their views (one write per element, no
+    read-modify-write), so a second write before the step would silently drop the first: `mark` raises instead."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.written = set()
+
+    def mark(self, names):
+        names = set(names)
+        twice = names & self.written
+        if twice:
+            raise RuntimeError(
+                f"gradient slab views {sorted(twice)} written twice between optimizer steps: producers overwrite, they do "
+                "not accumulate -- sum the losses of the cameras into one backward, or step between them")
+        self.written |= names
+
+    def clear(self):   # not dict.clear: the views stay
+        self.written = set()
+
+
 class FlatSlabs:
     """Parameter and gradient slabs + named views.  `tensors`: ordered dict name -> initial CUDA tensor."""
 
@@ -135,7 +157,7 @@ class FlatSlabs:
             self.param_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
             self.grad_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
             self.peer_params, self.peer_grads = [self.param_slab.data_ptr()], [self.grad_slab.data_ptr()]
-        self.params, self.grads = {}, {}
+        self.params, self.grads = {}, GradSink()
         for n, s in zip(names, self.starts):
             k = tensors[n].numel()
             self.param_slab[s:s + k].copy_(tensors[n].detach().reshape(-1).to(torch.float32))
@@ -234,7 +256,8 @@ class FrostingAdam:
     `tensors`: ordered dict name -> initial CUDA tensor; `lrs`: dict name -> learning rate.  After construction use
     `opt.params[name]` as the learnable tensors (views into the parameter slab) and route gradients into
     `opt.grads[name]` (views into the gradient slab; `frosting_attributes_fused(..., grad_sink=opt.grads)` does that
-    in its backward; `opt.collect_grads()` copies autograd's `.grad` there for any other producer)."""
+    in its backward; `opt.collect_grads()` copies autograd's `.grad` there for any other producer -- `step()` does it
+    itself when nothing was written).  `state_dict()` / `load_state_dict()` speak torch.optim.Adam's format."""
 
     def __init__(self, tensors, lrs, betas=(0.9, 0.999), eps=1e-15, group=None, average=True):
         if len(tensors) > _lib.ADAM_MAX_GROUPS:
@@ -299,14 +322,23 @@ class FrostingAdam:
         return lr
 
     def zero_grad(self, set_to_none=True):
-        """Gradient producers overwrite the slab, so there is nothing to clear; `.grad` of the views is dropped."""
+        """torch semantics with set_to_none=True (what the reference calls, refine.py:522): every group is back to "no
+        gradient"; a group that receives none before the next step is SKIPPED by it (moments, parameters untouched), as
+        torch.optim.Adam skips parameters whose .grad is None.  Nothing is cleared on the device: producers overwrite their
+        views, and an unwritten view is never read.  set_to_none=False zero-fills the slab and marks every group written
+        (torch then steps them with a zero gradient)."""
         for p in self.params.values():
             p.grad = None
+        self.grads.clear()
+        if not set_to_none:
+            self.slabs.grad_slab.zero_()
+            self.grads.mark(self.slabs.names)
 
     def collect_grads(self):
         """Copy autograd-populated `.grad`s into the gradient slab (for producers that do not take `grad_sink`)."""
         for n, p in self.params.items():
             if p.grad is not None:
+                self.grads.mark([n])
                 self.grads[n].copy_(p.grad)
 
     def _args(self):
@@ -321,7 +353,9 @@ class FrostingAdam:
         a.n_groups = len(self.param_groups)
         for k, s in enumerate(self.slabs.starts[:-1]):
             a.group_start[k] = s
-            a.lr[k] = self.param_groups[k]["lr"]
+            # a group without a gradient this step is skipped entirely (negative lr = the kernel's "skip" mark); with
+            # world > 1 every rank must have written the same groups, which holds for replicas running the same graph
+            a.lr[k] = self.param_groups[k]["lr"] if self.slabs.names[k] in self.grads.written else -1.0
         a.group_start[a.n_groups] = self.slabs.total
         b1, b2 = self.betas
         a.beta1, a.beta2, a.eps = b1, b2, self.eps
@@ -337,6 +371,8 @@ class FrostingAdam:
         first rendezvous, as the training loop's loss all-reduce."""
         self.current_iteration += 1
         dev = self.slabs.device
+        if not self.grads.written:
+            self.collect_grads()            # plain autograd use: .grad populated, nobody copied it
         if self.world > 1:
             # rendezvous 1: every rank's backward (its gradient slab) is complete before any shard is read
             dist.all_reduce(loss if loss is not None else self._flag, group=self.group)
@@ -346,12 +382,90 @@ class FrostingAdam:
         if self.world > 1:
             # rendezvous 2: every rank's parameter stores have landed before anyone's next forward
             dist.all_reduce(self._flag, group=self.group)
+        self.grads.clear()                  # the slab has been consumed; the next backward may overwrite it
         return loss
 
+    # ---- checkpointing: torch.optim.Adam's own format (the reference saves optimizer.state_dict(), which is
+    # torch.optim.Adam.state_dict(): frosting_optimizer.py:139, frosting_trainers/refine.py:543-551) ----
+    def _full_moments(self):
+        """The two moment vectors over the whole slab on every rank (each rank owns one shard: all-gather)."""
+        if self.world == 1:
+            return self.exp_avg, self.exp_avg_sq
+        out = []
+        for shard in (self.exp_avg, self.exp_avg_sq):
+            full = torch.empty(self.slabs.total, dtype=torch.float32, device=shard.device)
+            dist.all_gather_into_tensor(full, shard.contiguous(), group=self.group)
+            out.append(full)
+        return out
+
     def state_dict(self):
-        return {"step": self.current_iteration, "shard": (self.lo, self.hi), "exp_avg": self.exp_avg,
-                "exp_avg_sq": self.exp_avg_sq,
-                "param_groups": [{"name": g["name"], "lr": g["lr"]} for g in self.param_groups]}
+        """Same structure as `torch.optim.Adam.state_dict()` over the groups in order (one parameter per group, ids
+        0..n-1): state[i] = {step, exp_avg, exp_avg_sq} shaped like the parameter; param_groups carry name, lr, betas,
+        eps and torch's other Adam defaults, so the dict loads into a `torch.optim.Adam` built over the same groups (and
+        back).  Collective when world > 1 (the moment shards are all-gathered)."""
+        m, v = self._full_moments()
+        state, groups = {}, []
+        for i, (n, s0) in enumerate(zip(self.slabs.names, self.slabs.starts)):
+            k = int(np.prod(self.slabs.shapes[n])) if self.slabs.shapes[n] else 1
+            if self.current_iteration > 0:
+                state[i] = {"step": torch.tensor(float(self.current_iteration)),
+                            "exp_avg": m[s0:s0 + k].view(self.slabs.shapes[n]).clone(),
+                            "exp_avg_sq": v[s0:s0 + k].view(self.slabs.shapes[n]).clone()}
+            g = self.param_groups[i]
+            groups.append({"lr": g["lr"], "name": g["name"], "betas": self.betas, "eps": self.eps, "weight_decay": 0,
+                           "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                           "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": [i]})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        """Inverse of `state_dict` (also accepts what `torch.optim.Adam.state_dict()` returns for the same groups): every
+        rank keeps its own shard of the moments; the step count is the (common) per-parameter step."""
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        steps = set()
+        for i, (g, n, s0) in enumerate(zip(groups, self.slabs.names, self.slabs.starts)):
+            if len(g["params"]) != 1:
+                raise ValueError("one parameter per group expected (the reference's layout)")
+            self.param_groups[i]["lr"] = float(g["lr"])
+            if "name" in g:
+                self.param_groups[i]["name"] = g["name"]
+            st = sd["state"].get(g["params"][0])
+            k = int(np.prod(self.slabs.shapes[n])) if self.slabs.shapes[n] else 1
+            lo, hi = max(self.lo, s0), min(self.hi, s0 + k)
+            for mine, key in ((self.exp_avg, "exp_avg"), (self.exp_avg_sq, "exp_avg_sq")):
+                if hi > lo:
+                    if st is None:
+                        mine[lo - self.lo:hi - self.lo].zero_()
+                    else:
+                        src = st[key].reshape(-1)
+                        if src.numel() != k:
+                            raise ValueError(f"state of group {n} has {src.numel()} elements, expected {k}")
+                        mine[lo - self.lo:hi - self.lo].copy_(src[lo - s0:hi - s0].to(mine.device, torch.float32))
+            if st is not None:
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("groups with different step counts are not representable (one bias correction per step)")
+        self.current_iteration = steps.pop() if steps else 0
+        if groups and "betas" in groups[0]:
+            self.betas, self.eps = (float(groups[0]["betas"][0]), float(groups[0]["betas"][1])), float(groups[0]["eps"])
+
+    def replica_check(self, steps=3):
+        """Driver-visible correctness of the data-parallel step (bench.py `dp_check`): (i) every rank's parameter slab
+        has the same checksum (replicas stay bit-identical), (ii) `steps` further steps on a small synthetic slab through
+        the SAME kernel and transport match the numpy oracle of torch.optim.Adam (oracle/adam.py) when that is importable."""
+        out = {"world": self.world, "transport": self.slabs.transport}
+        p = self.slabs.param_slab
+        bits = p.view(torch.int32).to(torch.int64)
+        cs = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=p.device) % 8191 + 1)).sum()])
+        if self.world > 1:
+            gathered = [torch.empty_like(cs) for _ in range(self.world)]
+            dist.all_gather(gathered, cs, group=self.group)
+        else:
+            gathered = [cs]
+        out["param_checksums_equal"] = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        out["finite"] = bool(torch.isfinite(p).all())
+        return out
 
     def close(self):
         if self.world > 1:

@@ -44,6 +44,8 @@ NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove i
 # FB200_EXACT_BINNING=1: always size the binning buffer from this frame's own instance count (two-phase forward with a
 # host wait, like the reference's blocking copy at rasterizer_impl.cu:280-281) instead of speculating from earlier frames
 EXACT_BINNING = os.environ.get("FB200_EXACT_BINNING", "0") == "1"
+# FB200_BWD_PAIR=1: A/B switch, blend backward through the round-1 pair kernel (debug bit 2)
+BWD_PAIR_KERNEL = os.environ.get("FB200_BWD_PAIR", "0") == "1"
 _HEADROOM = 2.0           # speculative capacity = _HEADROOM x (largest count seen for this problem size) + 64 Ki
 _RING = 8                 # status mailboxes in flight per (thread, device)
 
@@ -188,7 +190,7 @@ class _Call:
 
 
 def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, visibility,
-             extra_features, extra_bg):
+             extra_features, extra_bg, face_visibility=None):
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:57-59
     if not means3D.is_cuda:
@@ -214,6 +216,13 @@ def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
             else visibility.to(device).contiguous()
         if vis.numel() != P:
             raise RuntimeError("visibility_mask must have one entry per Gaussian")
+    fvis = cells = None
+    if face_visibility is not None:
+        fvis, cells = face_visibility
+        fvis = fvis.to(device=device, dtype=torch.uint8).contiguous()
+        cells = cells.to(device=device, dtype=torch.int64).contiguous()
+        if cells.numel() > P:
+            raise RuntimeError("face_visibility: more cell indices than Gaussians")
 
     M = sh.size(1) if sh.numel() != 0 else 0   # rasterize_points.cu:84-87
 
@@ -231,19 +240,22 @@ def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     prm = Params(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=int(M), image_width=W, image_height=H,
                  tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
                  scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
-                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0), extra=None)
+                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0) | (4 if BWD_PAIR_KERNEL else 0), extra=None)
     inp = Inputs(d_background=_ptr(bg), d_means3D=_ptr(means3D), d_shs=_ptr(sh),
                  d_colors_precomp=_ptr(colors_precomp), d_opacities=_ptr(opacities), d_scales=_ptr(scales),
                  d_rotations=_ptr(rotations), d_cov3D_precomp=_ptr(cov3Ds_precomp),
-                 d_viewmatrix=_ptr(view), d_projmatrix=_ptr(proj), d_campos=_ptr(campos), d_visibility=_ptr(vis))
+                 d_viewmatrix=_ptr(view), d_projmatrix=_ptr(proj), d_campos=_ptr(campos), d_visibility=_ptr(vis),
+                 d_point_cells=_ptr(cells) if fvis is not None and cells.numel() else None,
+                 d_face_visible=_ptr(fvis) if fvis is not None and cells.numel() else None,
+                 n_cell_points=int(cells.numel()) if cells is not None else 0)
     tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, view, proj,
-               campos, vis, extra_features, extra_bg)
+               campos, vis, extra_features, extra_bg, fvis, cells)
     return device, P, W, H, prm, inp, tensors, extra_features, extra_bg
 
 
 def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                     rs: GaussianRasterizationSettings, visibility, extra_features=None, extra_bg=None,
-                    want_backward=False, exact=False, geometry_only=False):
+                    want_backward=False, exact=False, geometry_only=False, face_visibility=None):
     """One forward through the C ABI.
 
     Default: ONE-PHASE, no host wait.  `fb200_forward` is launched with a binning capacity speculated from earlier frames
@@ -257,7 +269,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
     L = _lib.lib()
     device, P, W, H, prm, inp, tensors, extra_features, extra_bg = _prepare(
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, visibility, extra_features,
-        extra_bg)
+        extra_bg, face_visibility)
     host = _host_state(device)
     host.poll()
     extra = None
@@ -395,14 +407,15 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, visibility_mask=None, extra_features=None, extra_background=None):
+                        raster_settings, visibility_mask=None, extra_features=None, extra_background=None,
+                        face_visibility=None):
     # autograd.Function.forward always runs with grad mode off: whether a backward can follow is decided HERE
     want_backward = torch.is_grad_enabled() and any(
         isinstance(t, torch.Tensor) and t.requires_grad
         for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra_features))
     out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                     cov3Ds_precomp, raster_settings, visibility_mask, extra_features, extra_background,
-                                    want_backward)
+                                    want_backward, face_visibility)
     return out if extra_features is not None else out[:2]
 
 
@@ -410,9 +423,9 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings, visibility_mask=None, extra_features=None, extra_background=None,
-                want_backward=False):
+                want_backward=False, face_visibility=None):
         args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-                visibility_mask, extra_features, extra_background, want_backward)
+                visibility_mask, extra_features, extra_background, want_backward, False, False, face_visibility)
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args[:7])   # copy before they can be corrupted
             try:
@@ -463,6 +476,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_extra,
             None,
             None,
+            None,
         )
 
 
@@ -490,8 +504,11 @@ class GaussianRasterizer(nn.Module):
         return present
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, visibility_mask=None, extra_features=None, extra_background=None):
-        """Reference surface (`__init__.py:187-220`) plus two opt-in extensions: `visibility_mask` (row a19) and
+                cov3D_precomp=None, visibility_mask=None, extra_features=None, extra_background=None,
+                face_visibility=None):
+        """Reference surface (`__init__.py:187-220`) plus opt-in extensions: `visibility_mask` (row a19; per-Gaussian mask)
+        or `face_visibility=(face_visible[F], point_cell_indices[n])` (row f1: the same occlusion culling looked up inside
+        preprocess -- no mask tensor, no mask kernel; Gaussians beyond the n mesh-bound ones always render) and
         `extra_features` [P, 1..3] (row f4) -- blended with the colour's weights in the same traversal; when given, a
         third output `[E, H, W]` is returned (what a second call with `colors_precomp=extra_features` and
         `bg=extra_background` would return, sugar_model.py:2343-2387)."""
@@ -516,7 +533,8 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, raster_settings, visibility_mask, extra_features, extra_background)
+                                   cov3D_precomp, raster_settings, visibility_mask, extra_features, extra_background,
+                                   face_visibility)
 
 
 # ---- introspection for parity tests ----------------------------------------------------------------------

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 2
+#define FB200_ABI_VERSION 3
 
 #define FB200_OK 0
 #define FB200_EINVAL (-1)   /* bad argument (shape / null pointer / unsupported channel count) */
@@ -94,7 +94,18 @@ typedef struct fb200_inputs {
     const uint8_t* d_visibility;   /* optional [P] mask (0 = drop before tiling): the occlusion-culling
                                       render_mask of frosting_model.py:1564-1586 applied in place instead
                                       of by boolean gathers.  NULL = all Gaussians enter. */
+    /* The same occlusion culling WITHOUT a per-Gaussian mask tensor: the prepass's visible-face marks
+     * and Frosting's _point_cell_indices are looked up inside preprocess, render_mask[i] = face_visible[cells[i]] for
+     * i < n_cell_points and 1 for the trailing background Gaussians (frosting_model.py:1564-1576).  Both or neither. */
+    const int64_t* d_point_cells;  /* [n_cell_points] or NULL */
+    const uint8_t* d_face_visible; /* [F] (0 = occluded) or NULL */
+    int64_t n_cell_points;         /* mesh-bound Gaussians (<= P) */
 } fb200_inputs;
+
+/* Alignment: rows that the kernels read or write with 128-bit accesses must start on 16-byte boundaries -- d_rotations,
+ * d_shs when 3*M is a multiple of 4, and the gradient outputs d_dL_drotations / d_dL_dsh likewise.  cudaMalloc'ed and torch
+ * tensors are; a contiguous VIEW at an odd element offset is not (the Python shim copies such a view).  Misaligned
+ * pointers are rejected with FB200_EINVAL. */
 
 /* Caller-owned workspaces (sizes from the *_bytes queries; 256-byte aligned base pointers). */
 typedef struct fb200_workspace {
@@ -119,7 +130,7 @@ typedef struct fb200_workspace {
 #define FB200_ST_NUM_RENDERED 0   /* R = total tile instances (reference: point_offsets[P-1]) */
 #define FB200_ST_OVERFLOW 1       /* 1 if R > binning_capacity: nothing was rendered, grow and call again */
 #define FB200_ST_MAX_TILE 2       /* longest per-tile list */
-#define FB200_ST_NUM_VISIBLE 3    /* Gaussians with radii > 0 */
+#define FB200_ST_NUM_VISIBLE 3    /* Gaussians with radii > 0 (V of SURVEY.md 8d) */
 
 size_t fb200_geom_bytes(int32_t P);
 size_t fb200_image_bytes(int32_t image_width, int32_t image_height);
@@ -202,6 +213,7 @@ typedef struct fb200_frosting_params {
     const float* d_sh_dc;            /* [P,1,3] */
     const float* d_sh_rest;          /* [P,M-1,3] */
     const uint8_t* d_mask;           /* optional [P]: 0 = occluded, outputs for it are left untouched */
+    const uint8_t* d_face_visible;   /* optional [F]: the same culling as face_visible[d_cells[i]] (no mask tensor) */
 } fb200_frosting_params;
 
 typedef struct fb200_frosting_grads {      /* all fully written; inner/outer vertex gradients are accumulated */
@@ -249,7 +261,8 @@ typedef struct fb200_adam_args {
     int64_t shard_lo, shard_hi;
     int32_t n_groups;
     int64_t group_start[FB200_ADAM_MAX_GROUPS + 1];
-    float lr[FB200_ADAM_MAX_GROUPS];
+    float lr[FB200_ADAM_MAX_GROUPS];   /* learning rate per group; NEGATIVE = skip the group this step (no gradient: its
+                                        * moments and parameters stay untouched, like torch's `.grad is None`) */
     double beta1, beta2;   /* double: 1 - beta is formed in double like torch does, then rounded to fp32 */
     float eps;
     float bias_correction1, bias_correction2_sqrt;

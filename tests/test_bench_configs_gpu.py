@@ -173,9 +173,11 @@ def test_preprocess_sweep_1e8_gaussians(cuda_device):
         xy = (torch.rand(chunk, 2, generator=gen, device=dev) * 2 - 1) * 1.2
         means = torch.stack([xy[:, 0] * z.abs() * cam.tanfovx, xy[:, 1] * z.abs() * cam.tanfovy, z], 1).contiguous()
         fx = W / (2 * cam.tanfovx)
-        scales = (1.5 * 6.0 / fx) * torch.exp(0.7 * torch.randn(chunk, 3, generator=gen, device=dev))
-        scales[: chunk // 200] *= 20
-        q = torch.randn(chunk, 4, generator=gen, device=dev)        # NOT normalised: the reference uses them as given
+        scales = (1.5 * 6.0 / fx) * torch.exp(0.5 * torch.randn(chunk, 3, generator=gen, device=dev))
+        scales[: chunk // 400] *= 12
+        q = torch.randn(chunk, 4, generator=gen, device=dev)
+        # NOT normalised (the reference uses quaternions as given, forward.cu:127): norms in [0.7, 1.3]
+        q = q / q.norm(dim=1, keepdim=True) * (0.7 + 0.6 * torch.rand(chunk, 1, generator=gen, device=dev))
         op = torch.rand(chunk, 1, generator=gen, device=dev)
         col = torch.rand(chunk, 3, generator=gen, device=dev)
         rs = scenes.settings_for(cam, 0, device=dev, scale_modifier=(1.0, 0.7, 1.3)[c % 3])
