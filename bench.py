@@ -375,6 +375,52 @@ def cpu_baseline(wl, step, sample_cam=0):
                        f"single thread, {dt:.1f} s"), f["binned"]["num_rendered"]
 
 
+def dp_oracle_check(device, world, rank):
+    """Driver-visible correctness of the data-parallel step (row f3): a small synthetic slab goes through the SAME kernel
+    and transport for 3 steps on all ranks with per-rank gradients; every rank's parameters must be bit-identical and
+    must match the numpy restatement of torch.optim.Adam over the rank-ordered gradient sum (oracle/adam.py::dp_step --
+    the oracle used as the checker, never as the thing measured)."""
+    import numpy as np
+    from frosting_b200 import optim
+    from oracle import adam as adam_oracle
+    shapes = {"a": (1001, 6), "b": (1001, 1, 3), "c": (1001, 15, 3), "d": (1001, 1), "e": (333,), "f": (1001, 4)}
+    lrs = {"a": 0.005, "b": 0.0025, "c": 0.000125, "d": 0.05, "e": 0.005, "f": 0.001}
+
+    def grads(t, r, k, n):
+        rng = np.random.default_rng(100000 * t + 100 * r + k)
+        g = rng.standard_normal(n).astype(np.float32) * (10.0 ** rng.integers(-6, 1, n)).astype(np.float32)
+        g[rng.random(n) < 0.3] = 0.0
+        return g
+    rng = np.random.default_rng(3)
+    init = {n: rng.standard_normal(sh).astype(np.float32) for n, sh in shapes.items()}
+    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(device) for n, x in init.items()}, lrs)
+    for t in range(1, 4):
+        for k, n in enumerate(shapes):
+            opt.grads[n].copy_(torch.from_numpy(grads(t, rank, k, init[n].size)).view(shapes[n]))
+        opt.step()
+    torch.cuda.synchronize(device)
+    mine = torch.cat([opt.params[n].detach().reshape(-1) for n in shapes])
+    if world > 1:
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+    else:
+        every = [mine]
+    identical = all(bool(torch.equal(e.view(torch.int32), every[0].view(torch.int32))) for e in every)
+    err = 0.0
+    for k, n in enumerate(shapes):
+        p, m, v = init[n].reshape(-1).copy(), np.zeros(init[n].size, np.float32), np.zeros(init[n].size, np.float32)
+        for t in range(1, 4):
+            p, m, v = adam_oracle.dp_step(p, [grads(t, r, k, init[n].size) for r in range(world)], m, v, lrs[n], t,
+                                          1.0 / world)
+        got = opt.params[n].detach().cpu().numpy().reshape(-1)
+        err = max(err, float(np.max(np.abs(got - p) / (5e-7 + 3e-6 * np.abs(p)))))
+    out = {"world": world, "transport": opt.slabs.transport, "replicas_bit_identical": identical,
+           "max_err_vs_oracle_in_tolerances": err, "pass": bool(identical and err <= 1.0),
+           "note": "3 steps of the reduce+Adam+publish kernel on a synthetic slab vs oracle/adam.py (rtol 3e-6, atol 5e-7)"}
+    opt.close()
+    return out
+
+
 def make_step(impl, wl, device, **kw):
     if impl == "ours":
         return cb.CameraBatch(wl, device, **kw)
@@ -596,12 +642,16 @@ def main():
                         "reference: NCCL all-reduce of each .grad + torch.optim.Adam)"}
             if ours:
                 out["dp_train_step"]["transport"] = dstep.opt.slabs.transport
-                if hasattr(dstep.opt, "replica_check"):
-                    try:
-                        out["dp_check"] = dstep.opt.replica_check()
-                    except Exception as ex:
-                        out["dp_check"] = {"error": repr(ex)}
+                try:
+                    chk = dstep.opt.replica_check()
+                except Exception as ex:
+                    chk = {"error": repr(ex)}
                 dstep.opt.close()
+                try:
+                    chk.update(dp_oracle_check(device, world, rank))
+                except Exception as ex:
+                    chk["oracle_check_error"] = repr(ex)
+                out["dp_check"] = chk
             del dstep
         except Exception as ex:
             out["dp_train_step_error"] = repr(ex)

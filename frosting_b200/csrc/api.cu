@@ -175,6 +175,7 @@ const char* fb200_last_error(void) { return g_err; }
 size_t fb200_geom_bytes(int32_t P) { return GeomLayout((size_t)(P < 0 ? 0 : P)).total; }
 size_t fb200_image_bytes(int32_t W, int32_t H) { return ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
 size_t fb200_binning_bytes(int64_t capacity) { return BinLayout((size_t)(capacity < 0 ? 0 : capacity)).total; }
+size_t fb200_rec_stream_bytes(int64_t capacity) { return (size_t)(capacity < 0 ? 0 : capacity) * sizeof(SplatRec) + 256; }
 
 int fb200_get_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, fb200_layout* out) {
     if (!out || P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(FB200_EINVAL, "bad layout query%s");
@@ -213,6 +214,7 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     a.clamped = reinterpret_cast<uint8_t*>(g + gl.clamped);
     a.final_T = reinterpret_cast<float*>(im + il.final_T);
     a.n_contrib = reinterpret_cast<uint32_t*>(im + il.n_contrib);
+    a.last_entry = reinterpret_cast<uint32_t*>(im + il.last_entry);
     a.ranges = reinterpret_cast<uint2*>(im + il.ranges);
     a.tile_count = reinterpret_cast<uint32_t*>(im + il.tile_count);
     a.cursor = reinterpret_cast<uint32_t*>(im + il.cursor);
@@ -224,7 +226,14 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     a.point_list = bn ? reinterpret_cast<uint32_t*>(bn + bl.point_list) : nullptr;
     a.keys = bn ? reinterpret_cast<unsigned long long*>(bn + bl.keys) : nullptr;
     a.keys_scratch = bn ? reinterpret_cast<unsigned long long*>(bn + bl.keys_scratch) : nullptr;
+    a.sub_hits = bn ? reinterpret_cast<uint32_t*>(bn + bl.sub_hits) : nullptr;
     a.capacity = ws->binning_capacity;
+    a.rec_stream = nullptr;
+    if ((prm->debug & 8) && ws->d_rec_stream) {
+        if (ws->rec_stream_bytes < fb200_rec_stream_bytes(ws->binning_capacity))
+            return fail(FB200_ENOSPC, "record stream workspace too small%s");
+        a.rec_stream = reinterpret_cast<SplatRec*>(align128(ws->d_rec_stream));
+    }
     a.status = ws->d_status;
     a.out_color = d_out_color;
     a.radii = d_radii;
@@ -314,8 +323,10 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     a.acc = reinterpret_cast<float*>(g + gl.acc);
     a.final_T = reinterpret_cast<const float*>(im + il.final_T);
     a.n_contrib = reinterpret_cast<const uint32_t*>(im + il.n_contrib);
+    a.last_entry = reinterpret_cast<const uint32_t*>(im + il.last_entry);
     a.ranges = reinterpret_cast<const uint2*>(im + il.ranges);
     a.point_list = bn ? reinterpret_cast<const uint32_t*>(bn + bl.point_list) : nullptr;
+    a.sub_hits = bn ? reinterpret_cast<const uint32_t*>(bn + bl.sub_hits) : nullptr;
     a.status = ws->d_status;
     a.radii = d_radii;
     a.dL_dpix = d_dL_dout_color;
@@ -343,13 +354,14 @@ int fb200_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmat
 
 int fb200_mesh_visibility(int32_t V, int32_t F, const float* d_verts, const int32_t* d_faces,
                           const float* d_full_proj, int32_t W, int32_t H, uint64_t* d_zbuf,
-                          int32_t* d_pix_to_face, uint8_t* d_face_visible, int32_t mark_last_on_bg, void* stream) {
+                          int32_t* d_pix_to_face, uint8_t* d_face_visible, int32_t mark_last_on_bg,
+                          int32_t* d_scratch, void* stream) {
     if (V < 0 || F < 0 || W <= 0 || H <= 0 || !d_full_proj || !d_zbuf || !d_pix_to_face ||
         (F > 0 && (!d_verts || !d_faces)))
         return fail(FB200_EINVAL, "mesh_visibility: bad arguments%s");
     return check(launch_mesh_visibility(V, F, d_verts, d_faces, d_full_proj, W, H,
                                         reinterpret_cast<unsigned long long*>(d_zbuf), d_pix_to_face,
-                                        d_face_visible, mark_last_on_bg, static_cast<cudaStream_t>(stream)),
+                                        d_face_visible, mark_last_on_bg, d_scratch, static_cast<cudaStream_t>(stream)),
                  "mesh_visibility");
 }
 

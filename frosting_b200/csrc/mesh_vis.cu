@@ -43,6 +43,15 @@ __device__ __forceinline__ ClipV lerp(const ClipV& a, const ClipV& b, float t) {
 
 struct ScreenV { float x, y, z; };   // window coordinates (pixel centres at +0.5), depth in [0,1]
 
+__device__ __forceinline__ ScreenV to_screen(const ClipV& c, int W, int H) {
+    const float iw = __frcp_rn(c.w);
+    ScreenV s;
+    s.x = fmul(fadd(fmul(fmul(c.x, iw), 0.5f), 0.5f), (float)W);
+    s.y = fmul(fadd(fmul(fmul(c.y, iw), 0.5f), 0.5f), (float)H);
+    s.z = fadd(fmul(fmul(c.z, iw), 0.5f), 0.5f);
+    return s;
+}
+
 // Edge function with canonical endpoint order so that the two triangles sharing an edge see exactly
 // opposite values (watertight, no double hits).
 __device__ __forceinline__ float edge_fn(const ScreenV& a, const ScreenV& b, float px, float py) {
@@ -99,27 +108,16 @@ __device__ void raster_triangle(ScreenV v0, ScreenV v1, ScreenV v2, int W, int H
     }
 }
 
-__device__ __forceinline__ ScreenV to_screen(const ClipV& c, int W, int H) {
-    const float iw = __frcp_rn(c.w);
-    ScreenV s;
-    s.x = fmul(fadd(fmul(fmul(c.x, iw), 0.5f), 0.5f), (float)W);
-    s.y = fmul(fadd(fmul(fmul(c.y, iw), 0.5f), 0.5f), (float)H);
-    s.z = fadd(fmul(fmul(c.z, iw), 0.5f), 0.5f);
-    return s;
-}
+// Clip-space setup of one face: up to two screen triangles (near-plane clipping by Sutherland-Hodgman).
+struct FaceTris {
+    ScreenV t[2][3];
+    int n;
+};
 
-template <int kGroup>
-__global__ void __launch_bounds__(256)
-raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces,
-                    const float* __restrict__ proj, int W, int H, int area_lo, int area_hi,
-                    u64* __restrict__ zbuf) {
-    __shared__ float m[16];
-    if (threadIdx.x < 16) m[threadIdx.x] = proj[threadIdx.x];
-    __syncthreads();
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long f = gtid / kGroup;
-    const int lane = (int)(gtid % kGroup);
-    if (f >= F) return;
+__device__ __forceinline__ FaceTris setup_face(long long f, const float* __restrict__ verts,
+                                               const int32_t* __restrict__ faces, const float* m, int W, int H) {
+    FaceTris out;
+    out.n = 0;
     const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
     ClipV c[3];
     c[0] = to_clip(m, verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]);
@@ -129,11 +127,11 @@ raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __res
     const float d0 = fadd(c[0].z, c[0].w), d1 = fadd(c[1].z, c[1].w), d2 = fadd(c[2].z, c[2].w);
     const bool in0 = d0 >= 0.f && c[0].w > 1e-12f, in1 = d1 >= 0.f && c[1].w > 1e-12f, in2 = d2 >= 0.f && c[2].w > 1e-12f;
     const int nin = (int)in0 + (int)in1 + (int)in2;
-    if (nin == 0) return;
+    if (nin == 0) return out;
     if (nin == 3) {
-        raster_triangle<kGroup>(to_screen(c[0], W, H), to_screen(c[1], W, H), to_screen(c[2], W, H), W, H,
-                                (int)f, lane, area_lo, area_hi, zbuf);
-        return;
+        out.t[0][0] = to_screen(c[0], W, H); out.t[0][1] = to_screen(c[1], W, H); out.t[0][2] = to_screen(c[2], W, H);
+        out.n = 1;
+        return out;
     }
     // Sutherland-Hodgman against the near plane: up to 4 vertices
     ClipV poly[4];
@@ -150,13 +148,92 @@ raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __res
             poly[np++] = p;
         }
     }
-    if (np < 3) return;
-    ScreenV s0 = to_screen(poly[0], W, H), s1 = to_screen(poly[1], W, H), s2 = to_screen(poly[2], W, H);
-    raster_triangle<kGroup>(s0, s1, s2, W, H, (int)f, lane, area_lo, area_hi, zbuf);
+    if (np < 3) return out;
+    const ScreenV s0 = to_screen(poly[0], W, H), s1 = to_screen(poly[1], W, H), s2 = to_screen(poly[2], W, H);
+    out.t[0][0] = s0; out.t[0][1] = s1; out.t[0][2] = s2;
+    out.n = 1;
     if (np == 4) {
-        ScreenV s3 = to_screen(poly[3], W, H);
-        raster_triangle<kGroup>(s0, s2, s3, W, H, (int)f, lane, area_lo, area_hi, zbuf);
+        out.t[1][0] = s0; out.t[1][1] = s2; out.t[1][2] = to_screen(poly[3], W, H);
+        out.n = 2;
     }
+    return out;
+}
+
+// Pixel-centre bounding-box area of a screen triangle (0 if it cannot cover a pixel centre), the size-class key.
+__device__ __forceinline__ long long bbox_area(const ScreenV& v0, const ScreenV& v1, const ScreenV& v2, int W, int H) {
+    const float minx = fminf(v0.x, fminf(v1.x, v2.x)), maxx = fmaxf(v0.x, fmaxf(v1.x, v2.x));
+    const float miny = fminf(v0.y, fminf(v1.y, v2.y)), maxy = fmaxf(v0.y, fmaxf(v1.y, v2.y));
+    const int x0 = max(0, (int)ceilf(minx - 0.5f)), x1 = min(W - 1, (int)floorf(maxx - 0.5f));
+    const int y0 = max(0, (int)ceilf(miny - 0.5f)), y1 = min(H - 1, (int)floorf(maxy - 0.5f));
+    if (x0 > x1 || y0 > y1) return 0;
+    return (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
+}
+
+constexpr int kSmallArea = 32, kMidArea = 8192;
+
+// Pass 1, one thread per face: small triangles (the overwhelming majority at ~1 M faces / 1080p) are rasterised on the
+// spot; a face with a larger triangle goes onto the warp list or the CTA list and is rasterised by pass 2 over that list
+// ONLY.  (Round 1 launched the warp and CTA classes over all F faces -- F x 256 threads that loaded, projected and
+// exited, mesh_vis.cu r1:206-221.)  lists = [n_mid, n_big, pad, pad | mid faces (F) | big faces (F)].
+__global__ void __launch_bounds__(256)
+classify_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                      const float* __restrict__ proj, int W, int H, u64* __restrict__ zbuf, int32_t* __restrict__ lists) {
+    __shared__ float m[16];
+    if (threadIdx.x < 16) m[threadIdx.x] = proj[threadIdx.x];
+    __syncthreads();
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const FaceTris ft = setup_face(f, verts, faces, m, W, H);
+    long long amax = 0;
+    for (int k = 0; k < ft.n; ++k) amax = max(amax, bbox_area(ft.t[k][0], ft.t[k][1], ft.t[k][2], W, H));
+    if (amax == 0) return;
+    if (amax <= kSmallArea) {
+        for (int k = 0; k < ft.n; ++k)
+            raster_triangle<1>(ft.t[k][0], ft.t[k][1], ft.t[k][2], W, H, (int)f, 0, 0, 0x7fffffff, zbuf);
+    } else if (amax <= kMidArea) {
+        lists[4 + atomicAdd(lists + 0, 1)] = (int32_t)f;
+    } else {
+        lists[4 + F + atomicAdd(lists + 1, 1)] = (int32_t)f;
+    }
+}
+
+// Pass 2: kGroup threads per LISTED face (32: a warp, 256: a CTA), striding over the list.
+template <int kGroup>
+__global__ void __launch_bounds__(256)
+raster_listed_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                           const float* __restrict__ proj, int W, int H, u64* __restrict__ zbuf,
+                           const int32_t* __restrict__ count, const int32_t* __restrict__ list) {
+    __shared__ float m[16];
+    if (threadIdx.x < 16) m[threadIdx.x] = proj[threadIdx.x];
+    __syncthreads();
+    const int n = *count;
+    const int groups_per_block = 256 / kGroup;
+    const int lane = threadIdx.x % kGroup;
+    for (long long i = (long long)blockIdx.x * groups_per_block + threadIdx.x / kGroup; i < n;
+         i += (long long)gridDim.x * groups_per_block) {
+        const long long f = list[i];
+        const FaceTris ft = setup_face(f, verts, faces, m, W, H);
+        for (int k = 0; k < ft.n; ++k)
+            raster_triangle<kGroup>(ft.t[k][0], ft.t[k][1], ft.t[k][2], W, H, (int)f, lane, 0, 0x7fffffff, zbuf);
+    }
+}
+
+// Without scratch space for the lists (d_scratch == NULL): every size class is launched over all faces.
+template <int kGroup>
+__global__ void __launch_bounds__(256)
+raster_faces_kernel(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                    const float* __restrict__ proj, int W, int H, int area_lo, int area_hi,
+                    u64* __restrict__ zbuf) {
+    __shared__ float m[16];
+    if (threadIdx.x < 16) m[threadIdx.x] = proj[threadIdx.x];
+    __syncthreads();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = gtid / kGroup;
+    const int lane = (int)(gtid % kGroup);
+    if (f >= F) return;
+    const FaceTris ft = setup_face(f, verts, faces, m, W, H);
+    for (int k = 0; k < ft.n; ++k)
+        raster_triangle<kGroup>(ft.t[k][0], ft.t[k][1], ft.t[k][2], W, H, (int)f, lane, area_lo, area_hi, zbuf);
 }
 
 __global__ void __launch_bounds__(256)
@@ -192,7 +269,7 @@ mask_from_faces_kernel(int n_points, const long long* __restrict__ cells, int F,
 
 cudaError_t launch_mesh_visibility(int V, int F, const float* verts, const int32_t* faces, const float* proj,
                                    int W, int H, unsigned long long* zbuf, int32_t* pix_to_face,
-                                   uint8_t* face_visible, int mark_last_on_bg, cudaStream_t s) {
+                                   uint8_t* face_visible, int mark_last_on_bg, int32_t* scratch, cudaStream_t s) {
     (void)V;
     const size_t N = (size_t)W * H;
     cudaError_t e = cudaMemsetAsync(zbuf, 0xff, N * 8, s);
@@ -201,25 +278,35 @@ cudaError_t launch_mesh_visibility(int V, int F, const float* verts, const int32
         e = cudaMemsetAsync(face_visible, 0, (size_t)F, s);
         if (e != cudaSuccess) return e;
     }
-    if (F > 0) {
-        const int kSmall = 32, kMid = 8192;
+    if (F > 0 && scratch != nullptr) {
+        e = cudaMemsetAsync(scratch, 0, 16, s);
+        if (e != cudaSuccess) return e;
+        classify_faces_kernel<<<(unsigned)(((long long)F + 255) / 256), 256, 0, s>>>(F, verts, faces, proj, W, H, zbuf,
+                                                                                     scratch);
+        // the lists live on the device: a fixed, SM-sized grid strides over whatever they hold (usually a few faces)
+        raster_listed_faces_kernel<32><<<148 * 2, 256, 0, s>>>(F, verts, faces, proj, W, H, zbuf, scratch + 0,
+                                                               scratch + 4);
+        raster_listed_faces_kernel<256><<<148, 256, 0, s>>>(F, verts, faces, proj, W, H, zbuf, scratch + 1,
+                                                            scratch + 4 + F);
+        count_launch(3);
+    } else if (F > 0) {
         {
             const long long threads = (long long)F;
             raster_faces_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
-                F, verts, faces, proj, W, H, 0, kSmall, zbuf);
+                F, verts, faces, proj, W, H, 0, kSmallArea, zbuf);
         }
         {
             const long long threads = (long long)F * 32;
             raster_faces_kernel<32><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
-                F, verts, faces, proj, W, H, kSmall, kMid, zbuf);
+                F, verts, faces, proj, W, H, kSmallArea, kMidArea, zbuf);
         }
         {
             const long long threads = (long long)F * 256;
             raster_faces_kernel<256><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
-                F, verts, faces, proj, W, H, kMid, 0x7fffffff, zbuf);
+                F, verts, faces, proj, W, H, kMidArea, 0x7fffffff, zbuf);
         }
+        count_launch(3);
     }
-    if (F > 0) count_launch(3);
     if (N > 0) count_launch();
     if (N > 0)
         resolve_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>((int)N, F, zbuf, pix_to_face, face_visible,

@@ -322,13 +322,17 @@ preprocess_fwd_kernel(FwdArgs a) {
                 // Conservative extents of {alpha >= 1/255}: |dx| > ext_x  =>  power < -t  for every dy,
                 // because max_dy power = -dx^2 / (2 Sigma_xx) and Sigma_xx = cov.x (culling).
                 // Margins cover the fp32 rounding of the reference's power/exp/alpha evaluation.
-                float ext_x, ext_y;
+                float ext_x, ext_y, thr;
                 {
                     const float t = logf(255.0f * opacity);
                     const float reach = Rf + 16.0f;
                     const float Sq = (fabsf(conic_x) + fabsf(conic_y) + fabsf(conic_z)) * reach * reach;
                     const float kappa = fabsf(cov.x * cov.z * det_inv);
                     const float tm = (t + 2e-3f + 1e-6f * Sq) * (1.0f + 2e-6f * kappa);
+                    // level of f = 0.5 (A dx^2 + C dy^2) + B dx dy above which no pixel contributes: tm, plus the rounding
+                    // of the exact test's own evaluation of f (same magnitude as the reference's, hence the same margin)
+                    thr = tm + 1e-3f + 1e-6f * Sq;
+                    if (!(thr == thr) || tm >= 1e30f) thr = __int_as_float(0x7f800000);
                     if (tm < 0.0f || opacity <= 0.0f) {
                         ext_x = __int_as_float(0xff800000); ext_y = ext_x;   // -inf: can never reach 1/255
                     } else if (tm >= 0.0f && tm < 1e30f) {
@@ -339,13 +343,13 @@ preprocess_fwd_kernel(FwdArgs a) {
                     } else {
                         ext_x = __int_as_float(0x7f800000); ext_y = ext_x;   // NaN/inf inputs: never cull
                     }
-                    if (a.prm.debug & 2) { ext_x = __int_as_float(0x7f800000); ext_y = ext_x; }
+                    if (a.prm.debug & 2) { ext_x = __int_as_float(0x7f800000); ext_y = ext_x; thr = ext_x; }
                 }
 
                 SplatRec r;
                 r.q0 = make_float4(pix_x, pix_y, conic_x, conic_y);
                 r.q1 = make_float4(conic_z, opacity, cr, cg);
-                r.q2 = make_float4(cb, ext_x, ext_y, depth);
+                r.q2 = make_float4(cb, ext_x, ext_y, thr);
                 a.rec[idx] = r;
                 a.depth[idx] = depth;
                 a.clamped[idx] = clamp_bits;
@@ -370,6 +374,15 @@ preprocess_fwd_kernel(FwdArgs a) {
     const unsigned vis = __ballot_sync(full, cnt != 0);
     if (vis == 0) return;
     if (lane == 0) atomicAdd(a.counters + 3, (uint32_t)__popc(vis));      // FB200_ST_NUM_VISIBLE
+    const uint32_t gxw = (uint32_t)a.tiles_x;
+    if (__reduce_max_sync(full, cnt) <= 24u) {
+        // small rectangles everywhere in the warp (the common frame): the plain per-lane walk is cheaper than the scan
+        const uint32_t maxy = rect.y >> 16, maxx = rect.y & 0xffffu;
+        if (cnt != 0)
+            for (uint32_t ty = miny; ty < maxy; ++ty)
+                for (uint32_t tx = minx; tx < maxx; ++tx) atomicAdd(a.tile_count + ty * gxw + tx, 1u);
+        return;
+    }
     uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -379,7 +392,6 @@ preprocess_fwd_kernel(FwdArgs a) {
     const uint32_t excl = incl - cnt;
     const uint32_t total = __shfl_sync(full, incl, 31);
     const float rw = w ? __frcp_rn((float)w) : 0.f;
-    const uint32_t gxw = (uint32_t)a.tiles_x;
     for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t item = base + lane;
         int pos = 0;                      // owner = number of lanes whose inclusive count is <= item

@@ -131,7 +131,7 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     if (32 + lane < n) id_next = point_list[range.x + (n - 1 - 32 - lane)];
 
     for (int base = 0; base < n; base += 32) {
-        const bool hit = (base + lane < n) && overlaps(lox, hix, r0.x, r2.y) && overlaps(loy, hiy, r0.y, r2.z);
+        const bool hit = (base + lane < n) && subtile_hit(lox, hix, loy, hiy, r0.x, r0.y, r0.z, r0.w, r1.x, r2.y, r2.z, r2.w);
         const uint32_t bits = __ballot_sync(full, hit);
         const int nhit = __popc(bits);
         if (hit) {
@@ -354,24 +354,25 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 // bank-conflict free.
 constexpr int kBlk = 16;            // Gaussians per block
 constexpr int kRow = 34;            // padded row length (floats) of the [kBlk][32 pixels] matrices
-constexpr int kQ = 64;              // hit queue capacity (>= kBlk - 1 + 32), power of two
 
 struct __align__(16) BwdWarpSmem {
     float m0[kBlk * kRow];          // masked opacity * G                       (phase 1 -> phase 3)
     float m1[kBlk * kRow];          // 1 / (1 - alpha)  -> T_g                  (phase 1 -> 2 -> 3)
     float m2[kBlk * kRow];          // alpha * (c . dL/dpix)  -> U              (phase 1 -> 2 -> 3)
     float dp0[32], dp1[32], dp2[32], K[32];     // per pixel: dL/dpixel, K = -T_final * (bg . dL/dpixel)
-    uint32_t last[32];                          // per pixel: n_contrib
-    float qx[kQ], qy[kQ], qA[kQ], qB[kQ], qC[kQ], qop[kQ], qr[kQ], qg[kQ], qb[kQ];   // hit queue (circular, SoA)
-    uint32_t qid[kQ], qpos[kQ];
+    uint32_t last[32];                          // per pixel: entries of the hit list up to its last contributor
 };
 
-template <int kWarps>
-__global__ void __launch_bounds__(32 * kWarps, 20 / kWarps)
-render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+// The list a warp walks is its sub-tile's HIT LIST, written by the forward blend (render_fwd.cu): the Gaussian ids
+// that passed the sub-tile test, in tile-list order, and per pixel the number of entries up to its last contributor.
+// The backward therefore touches no instance the forward did not blend into this sub-tile: no re-test, no walk over
+// the other 7/8 of the tile list, and the per-pixel "before my last contributor" test is a compare of entry numbers.
+template <int kWarps, int kResidentWarps>
+__global__ void __launch_bounds__(32 * kWarps, kResidentWarps / kWarps)
+render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ sub_hits,
                       const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
                       const float* __restrict__ bg, const float* __restrict__ final_T,
-                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
+                      const uint32_t* __restrict__ last_entry, const float* __restrict__ dL_dpix,
                       float* __restrict__ acc, const int32_t* __restrict__ status) {
     __shared__ BwdWarpSmem smem[kWarps];
     if (status[FB200_ST_OVERFLOW]) return;
@@ -383,26 +384,23 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int wslot = threadIdx.x >> 5;
     const int warp = (blockIdx.x % kSplit) * kWarps + wslot;      // sub-tile index inside the tile
     int lane;
-    unsigned lt_mask;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     BwdWarpSmem& sm = smem[wslot];
     const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
     const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
-    const float lox = (float)sub_x0, hix = (float)(sub_x0 + kSubW - 1);
-    const float loy = (float)sub_y0, hiy = (float)(sub_y0 + kSubH - 1);
     const uint2 range = ranges[tile];
+    const uint32_t* const sub = sub_hits + (size_t)kWarpsPerTile * range.x + (size_t)warp * (range.y - range.x);
 
     // ---- lane = pixel: the lane's own pixel, its recurrence state and its row of the per-pixel constants ----
     float T, E = 0.f, Kp;
-    int n;
+    int top;                        // entries [0, top) of the hit list are still to be processed
     {
         const int pix_x = sub_x0 + (lane & 7), pix_y = sub_y0 + (lane >> 3);
         const bool inside = pix_x < W && pix_y < H;
         const size_t pix_id = (size_t)pix_y * W + pix_x;
         const size_t HW = (size_t)H * W;
         const float T_final = inside ? final_T[pix_id] : 0.f;
-        const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+        const uint32_t le = inside ? last_entry[pix_id] : 0u;
         float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
         if (inside) {
             dp0 = dL_dpix[pix_id];
@@ -411,10 +409,10 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         }
         Kp = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
         T = T_final;
-        sm.dp0[lane] = dp0; sm.dp1[lane] = dp1; sm.dp2[lane] = dp2; sm.K[lane] = Kp; sm.last[lane] = last_contributor;
-        n = (int)__reduce_max_sync(full, last_contributor);
+        sm.dp0[lane] = dp0; sm.dp1[lane] = dp1; sm.dp2[lane] = dp2; sm.K[lane] = Kp; sm.last[lane] = le;
+        top = (int)__reduce_max_sync(full, le);
     }
-    if (n == 0) return;
+    if (top == 0) return;
     __syncwarp();
 
     // ---- lane = (Gaussian g, pixel half h): rows 2h, 2h+1 of the 8x4 sub-tile ----
@@ -430,15 +428,32 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const float* const pdp2 = sm.dp2 + 16 * h;
     const uint32_t* const plast = sm.last + 16 * h;
 
-    auto process_block = [&](int head, int cnt) {
+    // the next block's records are fetched while the current block is processed (one dependent hop: id -> record)
+    uint32_t nid = 0;
+    float4 n0, n1, n2;
+    n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int t) {       // entries t-1 ... t-16 (lane g takes entry t-1-g)
+        const int e = t - 1 - g;
+        if (e >= 0) {
+            nid = sub[e];
+            const float4* p = reinterpret_cast<const float4*>(rec + nid);
+            n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2);
+        }
+    };
+    fetch(top);
+
+    while (top > 0) {
+        const int cnt = min(kBlk, top);
         const bool valid = g < cnt;
-        const int slot = (head + g) & (kQ - 1);
-        const float X = sm.qx[slot], Y = sm.qy[slot], A = sm.qA[slot], B = sm.qB[slot], Cc = sm.qC[slot];
-        const float op = valid ? sm.qop[slot] : 0.f;
-        const float cr = valid ? sm.qr[slot] : 0.f, cg = valid ? sm.qg[slot] : 0.f, cb = valid ? sm.qb[slot] : 0.f;
-        const uint32_t pos = valid ? sm.qpos[slot] : 0xffffffffu;
-        const uint32_t gid = sm.qid[slot];
+        const uint32_t entry = (uint32_t)(top - 1 - g);          // this Gaussian's entry number (valid lanes)
+        const float X = n0.x, Y = n0.y, A = n0.z, B = n0.w, Cc = n1.x;
+        const float op = valid ? n1.y : 0.f;
+        const float cr = valid ? n1.z : 0.f, cg = valid ? n1.w : 0.f, cb = valid ? n2.x : 0.f;
+        const uint32_t gid = nid;
+        top -= cnt;
+        fetch(top);
         // ---- phase 1: alpha of (Gaussian g) x (16 pixels), the forward's op order ----
+        bool any_act = false;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const float dy = fadd(Y, -(py0 + (float)r));
@@ -452,10 +467,11 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 const P2 power = fma2(q, bc(-0.5f), neg2(u));
                 const P2 og = mul2(bc(op), exp_pair(power));
                 const uint2 lastp = *reinterpret_cast<const uint2*>(plast + k);
-                // contributes iff the forward blended it: before the pixel's last contributor, power <= 0, alpha >= 1/255
-                // (min(0.99, og) < 1/255  <=>  og < 1/255)
-                const bool a0 = (pos < lastp.x) && !(power.x > 0.0f) && !(og.x < 1.0f / 255.0f);
-                const bool a1 = (pos < lastp.y) && !(power.y > 0.0f) && !(og.y < 1.0f / 255.0f);
+                // contributes iff the forward blended it: not beyond the pixel's last contributor, power <= 0,
+                // alpha >= 1/255 (min(0.99, og) < 1/255  <=>  og < 1/255)
+                const bool a0 = valid && (entry < lastp.x) && !(power.x > 0.0f) && !(og.x < 1.0f / 255.0f);
+                const bool a1 = valid && (entry < lastp.y) && !(power.y > 0.0f) && !(og.y < 1.0f / 255.0f);
+                any_act |= a0 | a1;
                 const P2 ogm = p2(a0 ? og.x : 0.f, a1 ? og.y : 0.f);
                 const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
                 const P2 om = add2(bc(1.0f), neg2(am));                        // 1 - alpha in [0.01, 1]
@@ -473,19 +489,37 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 *reinterpret_cast<float2*>(row2 + k) = mul2(am, cd);
             }
         }
-        __syncwarp();
+        // Gaussians of the block with at least one contributing pixel (either half); the others are identities for the
+        // recurrences and add nothing to any sum
+        const unsigned act_bits = __ballot_sync(full, any_act);
+        const unsigned act16 = (act_bits | (act_bits >> 16)) & 0xffffu;
+        if (act16 == 0) continue;
+        __syncwarp();                  // phase 1's stores before phase 2's loads
         // ---- phase 2: lane = pixel, back-to-front recurrences over the block's Gaussians ----
         {
             float* c1 = sm.m1 + lane;
             float* c2 = sm.m2 + lane;
+            if (__popc(act16) + 2 >= cnt) {
+                // dense block: walk every row (inactive rows are identities: inv = 1, bb = 0), loads four deep
 #pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
-                const float inv = c1[i * kRow], bb = c2[i * kRow];
-                const float Tg = T * inv;                      // transmittance in front of Gaussian i at this pixel
-                c1[i * kRow] = Tg;
-                c2[i * kRow] = (Kp - E) * inv;                 // U: everything behind it (and the background) seen through it
-                E = fmaf(bb, Tg, E);
-                T = Tg;
+                for (int i = 0; i < cnt; ++i) {
+                    const float inv = c1[i * kRow], bb = c2[i * kRow];
+                    const float Tg = T * inv;                  // transmittance in front of Gaussian i at this pixel
+                    c1[i * kRow] = Tg;
+                    c2[i * kRow] = (Kp - E) * inv;             // U: everything behind it (and the background) seen through it
+                    E = fmaf(bb, Tg, E);
+                    T = Tg;
+                }
+            } else {
+                for (unsigned todo = act16; todo; todo &= todo - 1) {
+                    const int i = __ffs(todo) - 1;
+                    const float inv = c1[i * kRow], bb = c2[i * kRow];
+                    const float Tg = T * inv;
+                    c1[i * kRow] = Tg;
+                    c2[i * kRow] = (Kp - E) * inv;
+                    E = fmaf(bb, Tg, E);
+                    T = Tg;
+                }
             }
         }
         __syncwarp();
@@ -520,7 +554,7 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       sO.x + sO.y, sR.x + sR.y, sG.x + sG.y, sB.x + sB.y};
 #pragma unroll
         for (int i = 0; i < 9; ++i) v[i] += __shfl_xor_sync(full, v[i], 16);
-        if (h == 0 && valid) {
+        if (h == 0 && ((act16 >> g) & 1u)) {
             float* a = acc + (size_t)gid * 12;
             // dG/ddelx = -G (dx A + dy B), dG/ddely = -G (dy C + dx B)   (backward.cu:536-546)
             atomicAdd(a + 0, -ddelx_dx * fmaf(A, v[0], B * v[1]));
@@ -533,44 +567,8 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             atomicAdd(a + 7, v[7]);
             atomicAdd(a + 8, v[8]);
         }
-        __syncwarp();      // the matrices and the queue slots are rewritten next
-    };
-
-    // ---- walk the tile list back to front from the sub-tile's deepest last contributor, 32 instances per step ----
-    int head = 0, tail = 0;
-    uint32_t id_cur = 0, id_next = 0;
-    float4 r0, r1, r2;
-    r0 = r1 = r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < n) {
-        id_cur = point_list[range.x + (n - 1 - lane)];
-        const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
-        r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
+        __syncwarp();      // the matrices are rewritten by the next block
     }
-    if (32 + lane < n) id_next = point_list[range.x + (n - 1 - 32 - lane)];
-    for (int base = 0; base < n; base += 32) {
-        const bool hit = (base + lane < n) && overlaps(lox, hix, r0.x, r2.y) && overlaps(loy, hiy, r0.y, r2.z);
-        const uint32_t bits = __ballot_sync(full, hit);
-        if (hit) {
-            const int slot = (tail + __popc(bits & lt_mask)) & (kQ - 1);
-            sm.qx[slot] = r0.x; sm.qy[slot] = r0.y; sm.qA[slot] = r0.z; sm.qB[slot] = r0.w;
-            sm.qC[slot] = r1.x; sm.qop[slot] = r1.y; sm.qr[slot] = r1.z; sm.qg[slot] = r1.w; sm.qb[slot] = r2.x;
-            sm.qid[slot] = id_cur;
-            sm.qpos[slot] = (uint32_t)(n - 1 - base - lane);
-        }
-        tail += __popc(bits);
-        id_cur = id_next;
-        if (base + 32 + lane < n) {
-            const float4* p = reinterpret_cast<const float4*>(rec + id_cur);
-            r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2);
-        }
-        if (base + 64 + lane < n) id_next = point_list[range.x + (n - 1 - base - 64 - lane)];
-        __syncwarp();
-        while (tail - head >= kBlk) {
-            process_block(head, kBlk);
-            head += kBlk;
-        }
-    }
-    if (tail > head) process_block(head, tail - head);
 }
 
 }  // namespace
@@ -592,10 +590,14 @@ cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
         render_bwd_pair_kernel<false, kWarps><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
             a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+    else if (a.prm.debug & 16)      // A/B switch: 20 resident warps (<= 102 registers, no spills) instead of 24 (80, spills)
+        render_bwd_t16_kernel<kWarps, 20><<<grid, 32 * kWarps, 0, s>>>(
+            a.ranges, a.sub_hits, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
+            a.final_T, a.last_entry, a.dL_dpix, a.acc, a.status);
     else
-        render_bwd_t16_kernel<kWarps><<<grid, 32 * kWarps, 0, s>>>(
-            a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
-            a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status);
+        render_bwd_t16_kernel<kWarps, 24><<<grid, 32 * kWarps, 0, s>>>(
+            a.ranges, a.sub_hits, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
+            a.final_T, a.last_entry, a.dL_dpix, a.acc, a.status);
     return cudaGetLastError();
 }
 

@@ -65,8 +65,8 @@ class _FrostingAttributes(torch.autograd.Function):
         if ctx.sink is not None:
             # gradients go straight into the optimizer's gradient slab (frosting_b200/optim.py); autograd gets None
             k = ctx.sink
-            if hasattr(k, "mark"):
-                k.mark(("bary_logits", "opacity_logits", "log_scales", "quats", "sh_dc", "sh_rest"))
+            if hasattr(k, "sink_once"):
+                k.sink_once(("bary_logits", "opacity_logits", "log_scales", "quats", "sh_dc", "sh_rest"))
             d_bary, d_op, d_ls = k["bary_logits"], k["opacity_logits"], k["log_scales"]
             d_q, d_dc, d_rest = k["quats"], k["sh_dc"], k["sh_rest"]
             for t, ref in ((d_bary, bary_logits), (d_op, opacity_logits), (d_ls, log_scales), (d_q, quats),

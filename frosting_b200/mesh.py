@@ -34,7 +34,7 @@ def _verts_faces(mesh=None, verts=None, faces=None):
 
 
 def rasterize_mesh(verts: torch.Tensor, faces: torch.Tensor, full_proj_transform: torch.Tensor,
-                   image_height: int, image_width: int, mark_last_on_bg: bool = False):
+                   image_height: int, image_width: int, mark_last_on_bg: bool = False, work_lists: bool = True):
     """Nearest-face id per pixel and per-face visibility.
 
     Returns (pix_to_face int32 [H,W] with -1 for background, face_visible bool [F], zkeys int64 [H,W]).
@@ -49,11 +49,13 @@ def rasterize_mesh(verts: torch.Tensor, faces: torch.Tensor, full_proj_transform
         zbuf = torch.empty((H, W), dtype=torch.int64, device=device)
         pix_to_face = torch.empty((H, W), dtype=torch.int32, device=device)
         face_visible = torch.empty((max(F, 1),), dtype=torch.uint8, device=device)
+        scratch = torch.empty((2 * F + 4,), dtype=torch.int32, device=device) if (work_lists and F) else None
         _lib.check(_lib.lib().fb200_mesh_visibility(
             verts.shape[0], F, C.c_void_p(verts.data_ptr()) if F else None,
             C.c_void_p(faces.data_ptr()) if F else None, C.c_void_p(proj.data_ptr()), W, H,
             C.c_void_p(zbuf.data_ptr()), C.c_void_p(pix_to_face.data_ptr()),
             C.c_void_p(face_visible.data_ptr()), int(bool(mark_last_on_bg)),
+            C.c_void_p(scratch.data_ptr()) if scratch is not None else None,
             C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
     return pix_to_face, face_visible[:F].bool(), zbuf
 

@@ -104,24 +104,32 @@ def _view(ptr, n, device):
 
 class GradSink(dict):
     """name -> view into the gradient slab, plus the book-keeping torch keeps in `.grad is None`: which groups have
-    received a gradient since the last step / zero_grad.  Producers OVERWRITE their views (one write per element, no
-    read-modify-write), so a second write before the step would silently drop the first: `mark` raises instead."""
+    a gradient this step.  Fetching a view (`sink[name]`) declares that the group receives one -- every producer
+    gets its destination that way -- and `step()` skips the groups nobody fetched since the last step / zero_grad.
+    Producers OVERWRITE their views (one write per element, no read-modify-write), so a second fused backward into
+    the sink before the step would silently drop the first: `sink_once` raises instead."""
 
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
         self.written = set()
+        self.sunk = set()
 
-    def mark(self, names):
+    def __getitem__(self, name):
+        self.written.add(name)
+        return super().__getitem__(name)
+
+    def sink_once(self, names):
         names = set(names)
-        twice = names & self.written
+        twice = names & self.sunk
         if twice:
             raise RuntimeError(
                 f"gradient slab views {sorted(twice)} written twice between optimizer steps: producers overwrite, they do "
                 "not accumulate -- sum the losses of the cameras into one backward, or step between them")
-        self.written |= names
+        self.sunk |= names
 
     def clear(self):   # not dict.clear: the views stay
         self.written = set()
+        self.sunk = set()
 
 
 class FlatSlabs:
@@ -332,13 +340,12 @@ class FrostingAdam:
         self.grads.clear()
         if not set_to_none:
             self.slabs.grad_slab.zero_()
-            self.grads.mark(self.slabs.names)
+            self.grads.written = set(self.slabs.names)
 
     def collect_grads(self):
         """Copy autograd-populated `.grad`s into the gradient slab (for producers that do not take `grad_sink`)."""
-        for n, p in self.params.items():
+        for n, p in list(self.params.items()):
             if p.grad is not None:
-                self.grads.mark([n])
                 self.grads[n].copy_(p.grad)
 
     def _args(self):

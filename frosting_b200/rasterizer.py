@@ -46,6 +46,9 @@ NO_CULL = False   # test hook: disable sub-tile culling (debug bit 1) to prove i
 EXACT_BINNING = os.environ.get("FB200_EXACT_BINNING", "0") == "1"
 # FB200_BWD_PAIR=1: A/B switch, blend backward through the round-1 pair kernel (debug bit 2)
 BWD_PAIR_KERNEL = os.environ.get("FB200_BWD_PAIR", "0") == "1"
+# FB200_FWD_TMA=1: A/B switch, forward blend staged by 1-D cp.async.bulk copies of a packed record stream (debug bit 3)
+FWD_TMA = os.environ.get("FB200_FWD_TMA", "0") == "1"
+BWD_OCC20 = os.environ.get("FB200_BWD_OCC20", "0") == "1"      # A/B: backward blend at 20 resident warps / SM (debug bit 4)
 _HEADROOM = 2.0           # speculative capacity = _HEADROOM x (largest count seen for this problem size) + 64 Ki
 _RING = 8                 # status mailboxes in flight per (thread, device)
 
@@ -240,7 +243,7 @@ def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     prm = Params(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=int(M), image_width=W, image_height=H,
                  tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
                  scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
-                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0) | (4 if BWD_PAIR_KERNEL else 0), extra=None)
+                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0) | (4 if BWD_PAIR_KERNEL else 0) | (8 if FWD_TMA else 0) | (16 if BWD_OCC20 else 0), extra=None)
     inp = Inputs(d_background=_ptr(bg), d_means3D=_ptr(means3D), d_shs=_ptr(sh),
                  d_colors_precomp=_ptr(colors_precomp), d_opacities=_ptr(opacities), d_scales=_ptr(scales),
                  d_rotations=_ptr(rotations), d_cov3D_precomp=_ptr(cov3Ds_precomp),
@@ -251,6 +254,15 @@ def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, view, proj,
                campos, vis, extra_features, extra_bg, fvis, cells)
     return device, P, W, H, prm, inp, tensors, extra_features, extra_bg
+
+
+def _attach_stream(L, ws, capacity, device):
+    """TMA A/B only: the packed record stream workspace (48 B per tile instance)."""
+    if not FWD_TMA:
+        return None
+    buf = torch.empty((L.fb200_rec_stream_bytes(capacity),), dtype=torch.uint8, device=device)
+    ws.d_rec_stream, ws.rec_stream_bytes = buf.data_ptr(), buf.numel()
+    return buf
 
 
 def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -312,6 +324,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
             if not geometry_only:
                 binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
                 ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
+                stream_buf = _attach_stream(L, ws, capacity, device)
                 ws.h_status = mailbox.data_ptr()     # the host HAS this frame's status words: empty sort classes are skipped
                 _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
                                                   C.c_void_p(out_color.data_ptr()), rptr, sptr))
@@ -322,6 +335,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
             capacity = hint
             binning = torch.empty((L.fb200_binning_bytes(capacity),), dtype=torch.uint8, device=device)
             ws.d_binning, ws.binning_bytes, ws.binning_capacity = binning.data_ptr(), binning.numel(), capacity
+            stream_buf = _attach_stream(L, ws, capacity, device)
             _lib.check(L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws), C.c_void_p(out_color.data_ptr()),
                                        rptr, sptr))
             mailbox.copy_(status, non_blocking=True)
@@ -408,22 +422,23 @@ def cpu_deep_copy_tuple(input_tuple):
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings, visibility_mask=None, extra_features=None, extra_background=None,
-                        face_visibility=None):
+                        face_visibility=None, return_alpha=False):
     # autograd.Function.forward always runs with grad mode off: whether a backward can follow is decided HERE
     want_backward = torch.is_grad_enabled() and any(
         isinstance(t, torch.Tensor) and t.requires_grad
         for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, extra_features))
     out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                     cov3Ds_precomp, raster_settings, visibility_mask, extra_features, extra_background,
-                                    want_backward, face_visibility)
-    return out if extra_features is not None else out[:2]
+                                    want_backward, face_visibility, return_alpha)
+    res = out[:3] if extra_features is not None else out[:2]
+    return res + (out[3],) if return_alpha else res
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings, visibility_mask=None, extra_features=None, extra_background=None,
-                want_backward=False, face_visibility=None):
+                want_backward=False, face_visibility=None, return_alpha=False):
         args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
                 visibility_mask, extra_features, extra_background, want_backward, False, False, face_visibility)
         if raster_settings.debug:
@@ -443,10 +458,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.mark_non_differentiable(radii)
         if extra is None:
             extra = color.new_empty(0)        # placeholder third output (autograd wants tensors)
-        return color, radii, extra
+        # alpha = 1 - final_T: the reference computes and keeps final_T (forward.cu:369, imgBuffer) but never returns it
+        alpha = color.new_empty(0)
+        if return_alpha:
+            H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+            lay = Layout()
+            _lib.check(_lib.lib().fb200_get_layout(call.prm.P, W, H, 0, C.byref(lay)))
+            base = (-call.image.data_ptr()) % 128
+            final_T = call.image[base + lay.img_final_T: base + lay.img_final_T + W * H * 4].view(torch.float32).view(H, W)
+            alpha = 1.0 - final_T
+        ctx.mark_non_differentiable(alpha)
+        return color, radii, extra, alpha
 
     @staticmethod
-    def backward(ctx, grad_out_color, _, grad_out_extra=None):
+    def backward(ctx, grad_out_color, _, grad_out_extra=None, _alpha=None):
         (radii,) = ctx.saved_tensors
         call = ctx.call
         if ctx.raster_settings.debug:
@@ -474,6 +499,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             None,
             None,
             grad_extra,
+            None,
             None,
             None,
             None,
@@ -505,10 +531,12 @@ class GaussianRasterizer(nn.Module):
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None, visibility_mask=None, extra_features=None, extra_background=None,
-                face_visibility=None):
+                face_visibility=None, return_alpha=False):
         """Reference surface (`__init__.py:187-220`) plus opt-in extensions: `visibility_mask` (row a19; per-Gaussian mask)
         or `face_visibility=(face_visible[F], point_cell_indices[n])` (row f1: the same occlusion culling looked up inside
-        preprocess -- no mask tensor, no mask kernel; Gaussians beyond the n mesh-bound ones always render) and
+        preprocess -- no mask tensor, no mask kernel; Gaussians beyond the n mesh-bound ones always render),
+        `return_alpha=True` (appends the accumulated opacity 1 - final_T [H,W], detached -- the alpha of BASELINE's
+        "RGB/depth/alpha"; a DIFFERENTIABLE alpha is `extra_features=ones[P,1]`, depth is `extra_features=view-space z`) and
         `extra_features` [P, 1..3] (row f4) -- blended with the colour's weights in the same traversal; when given, a
         third output `[E, H, W]` is returned (what a second call with `colors_precomp=extra_features` and
         `bg=extra_background` would return, sugar_model.py:2343-2387)."""
@@ -534,7 +562,7 @@ class GaussianRasterizer(nn.Module):
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                    cov3D_precomp, raster_settings, visibility_mask, extra_features, extra_background,
-                                   face_visibility)
+                                   face_visibility, return_alpha)
 
 
 # ---- introspection for parity tests ----------------------------------------------------------------------

@@ -123,6 +123,10 @@ typedef struct fb200_workspace {
     const int32_t* h_status;               /* optional HOST copy of the status words written by fb200_forward_geometry,
                                               read by the caller after synchronising the stream; fb200_forward_raster
                                               then skips launches it can tell are empty.  NULL: launch for the worst case */
+    void* d_rec_stream; size_t rec_stream_bytes;  /* optional, fb200_rec_stream_bytes(binning_capacity): when given (and
+                                              prm->debug bit 3 is set) the forward blend runs the TMA-staged variant -- a
+                                              packed 48-byte record stream in sorted order, staged into shared memory
+                                              by 1-D cp.async.bulk copies (BASELINE north star; profiles/r02_tma_ab.md) */
 } fb200_workspace;
 
 /* d_status words written by fb200_forward (stream-ordered; copy back after the call). */
@@ -135,6 +139,7 @@ typedef struct fb200_workspace {
 size_t fb200_geom_bytes(int32_t P);
 size_t fb200_image_bytes(int32_t image_width, int32_t image_height);
 size_t fb200_binning_bytes(int64_t capacity);
+size_t fb200_rec_stream_bytes(int64_t capacity);
 
 /* Forward: preprocess + cull, per-tile bin/sort, front-to-back blend.
  *   d_out_color [3,H,W] f32, d_radii [P] i32 -- both fully written (no zero-fill needed).
@@ -183,11 +188,14 @@ int fb200_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmat
  *   d_pix_to_face [H*W] i32 : face id or -1 (mesh_rasterization.py:146 `rast_out[...,3] - 1`)
  *   d_face_visible [F] u8 (optional) : 1 if the face owns at least one pixel; if `mark_last_on_bg`
  *     the last face is also marked when any pixel is background, reproducing the `_index_mask[-1]`
- *     quirk of frosting_model.py:1565-1570. */
+ *     quirk of frosting_model.py:1565-1570.
+ *   d_scratch [2*F + 4] i32 (optional): work lists of the faces that need a warp / a CTA; with it one pass classifies
+ *     every face (rasterising the small ones on the spot) and the two larger classes run over their lists only; NULL:
+ *     every size class is launched over all F faces. */
 int fb200_mesh_visibility(int32_t V, int32_t F, const float* d_verts, const int32_t* d_faces,
                           const float* d_full_proj, int32_t image_width, int32_t image_height,
                           uint64_t* d_zbuf, int32_t* d_pix_to_face, uint8_t* d_face_visible,
-                          int32_t mark_last_on_bg, void* stream);
+                          int32_t mark_last_on_bg, int32_t* d_scratch, void* stream);
 
 /* render_mask[i] = face_visible[cell[i]] for i < n_cells_points, 1 for the trailing background
  * Gaussians (frosting_model.py:1571-1576). */

@@ -32,10 +32,10 @@ def test_workspace_size_queries_are_host_only_and_monotonic():
     g1, g2 = L.fb200_geom_bytes(1000), L.fb200_geom_bytes(2000)
     assert g2 > g1 >= 1000 * 109
     i1 = L.fb200_image_bytes(1920, 1080)
-    assert i1 >= 1920 * 1080 * 8 + 8160 * 8
+    assert i1 >= 1920 * 1080 * 12 + 8160 * 8
     assert L.fb200_image_bytes(1921, 1080) > i1
     b = L.fb200_binning_bytes(10_000)
-    assert 10_000 * 20 <= b <= 10_000 * 20 + 1024
+    assert 10_000 * 52 <= b <= 10_000 * 52 + 1024      # 20 B of keys + 8 sub-tile hit lists of 4 B per instance
 
 
 def test_layout_offsets_are_aligned_and_ordered():

@@ -156,3 +156,75 @@ def test_peer_memory_dp_adam_world2(multicast):
             gs = [_grads(t, 10 * r + k, init[n].size) for r in range(world)]
             p, m, v = adam_oracle.dp_step(p, gs, m, v, LRS[n], t, 0.5)
         np.testing.assert_allclose(res[0][n], p, rtol=3e-6, atol=5e-7)
+
+
+def test_state_dict_round_trips_through_torch_adam():
+    """the reference checkpoints `optimizer.state_dict()` = torch.optim.Adam's (frosting_optimizer.py:139,
+    refine.py:543-551).  Ours has the same format: it loads into a torch Adam over the same groups and back, and both
+    continue identically."""
+    from frosting_b200 import optim
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    init = {n: rng.standard_normal(s).astype(np.float32) for n, s in SHAPES.items()}
+    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(dev) for n, x in init.items()}, LRS)
+    assert opt.state_dict()["state"] == {}
+    for t in range(1, 4):
+        for k, n in enumerate(SHAPES):
+            opt.grads[n].copy_(torch.from_numpy(_grads(t, k, init[n].size)).view(SHAPES[n]))
+        opt.step()
+    sd = opt.state_dict()
+    assert sorted(sd) == ["param_groups", "state"] and len(sd["param_groups"]) == len(SHAPES)
+    # -> torch.optim.Adam over the same values
+    ref_p = {n: opt.params[n].detach().clone().requires_grad_(True) for n in SHAPES}
+    ref = torch.optim.Adam([{"params": [ref_p[n]], "lr": LRS[n]} for n in SHAPES], lr=0.0, eps=1e-15)
+    ref.load_state_dict(sd)
+    # -> a fresh FrostingAdam from what torch saves
+    opt2 = optim.FrostingAdam({n: opt.params[n].detach().clone() for n in SHAPES}, {n: 0.0 for n in SHAPES})
+    opt2.load_state_dict(ref.state_dict())
+    assert opt2.current_iteration == 3 and [g["lr"] for g in opt2.param_groups] == [LRS[n] for n in SHAPES]
+    for k, n in enumerate(SHAPES):
+        g = _grads(9, k, init[n].size)
+        for o in (opt, opt2):
+            o.grads[n].copy_(torch.from_numpy(g).view(SHAPES[n]))
+        ref_p[n].grad = torch.from_numpy(g.copy()).view(SHAPES[n]).to(dev)
+    opt.step(); opt2.step(); ref.step()
+    for n in SHAPES:
+        a = opt.params[n].detach().cpu().numpy().reshape(-1)
+        np.testing.assert_array_equal(a, opt2.params[n].detach().cpu().numpy().reshape(-1))
+        np.testing.assert_allclose(a, ref_p[n].detach().cpu().numpy().reshape(-1), rtol=3e-6, atol=5e-7)
+
+
+def test_groups_without_a_gradient_are_skipped_and_double_sink_raises():
+    """torch.optim.Adam skips parameters whose .grad is None; a stale slab must never be applied twice."""
+    import frosting_b200 as fb
+    from frosting_b200 import optim, scenes
+    dev = torch.device("cuda:0")
+    init = {n: torch.randn(s, generator=torch.Generator().manual_seed(1)).to(dev) for n, s in SHAPES.items()}
+    opt = optim.FrostingAdam(init, LRS)
+    for n in SHAPES:
+        opt.grads[n].fill_(0.5)
+    opt.step()
+    after1 = {n: opt.params[n].detach().clone() for n in SHAPES}
+    # second step: only "a" and "d" get a gradient (through autograd's .grad, collected by step())
+    opt.zero_grad()
+    (opt.params["a"].sum() * 2.0 + opt.params["d"].sum()).backward()
+    opt.step()
+    for n in SHAPES:
+        same = torch.equal(opt.params[n].detach(), after1[n])
+        assert same == (n not in ("a", "d")), n
+    # two fused backwards into the sink between steps
+    P = 2_000
+    cam = scenes.make_camera(64, 48, device=dev)
+    params, mesh = scenes.frosting_layer(P, cam, 5, n_faces_target=500, device=dev)
+    fo = optim.FrostingAdam.for_frosting(params)
+    for i in range(2):
+        out = fb.frosting_attributes_fused(fo.params, mesh, grad_sink=fo.grads)
+        loss = sum(v.sum() for v in out.values())
+        if i == 0:
+            loss.backward()
+        else:
+            with pytest.raises(RuntimeError, match="written twice"):
+                loss.backward()
+    fo.step()
+    out = fb.frosting_attributes_fused(fo.params, mesh, grad_sink=fo.grads)
+    sum(v.sum() for v in out.values()).backward()        # after a step the sink accepts the next backward

@@ -76,6 +76,10 @@ def test_mesh_prepass_cuda_matches_c_restatement(cuda_device):
                                        mark_last_on_bg=True)
         diff = (p2f.cpu().numpy() != p2f_c).mean()
         assert diff == 0.0, (case, diff)
+        # the work-list path (default) and the every-class-over-all-faces path are the same rasteriser
+        p2f_all, fv_all, _ = fb.rasterize_mesh(verts.to(dev), faces.to(dev), cam.full_proj_transform.to(dev), H, W,
+                                               mark_last_on_bg=True, work_lists=False)
+        assert torch.equal(p2f_all, p2f) and torch.equal(fv_all, fv), case
         assert np.array_equal(fv.cpu().numpy(), fv_c), case
         assert (p2f_c >= 0).any(), case
     # MeshRasterizer surface (frosting_utils/mesh_rasterization.py:109-172): shapes, -1 background, +1 convention

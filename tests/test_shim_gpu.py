@@ -1,0 +1,163 @@
+"""GPU tests of the host shim's round-2 behaviour: speculative one-phase forward and its overflow protocol, the
+in-kernel visible-face lookup (row f1), unaligned views, per-thread host state, the alpha output."""
+import threading
+
+import pytest
+import torch
+
+import frosting_b200 as fb
+from frosting_b200 import rasterizer as fbr
+from frosting_b200 import scenes
+from tests.util import scene, rel_err_stats
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("means3D", "opacities", "shs", "scales", "rotations")
+
+
+def _fwd_bwd(rs, g, cot, **kw):
+    leaves = {k: g[k].detach().clone().requires_grad_(True) for k in KEYS}
+    m2 = torch.zeros(leaves["means3D"].shape[0], 3, device=cot.device, requires_grad=True)
+    out = fb.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                    shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"], **kw)
+    (out[0] * cot).sum().backward()
+    return out, {k: v.grad for k, v in leaves.items()}
+
+
+def test_speculative_forward_equals_exact_and_overflow_is_loud(cuda_device):
+    dev = cuda_device
+    P, W, H = 60_000, 400, 304
+    cam, g, rs = scene(P, W, H, 31, 3, dev)
+    cot = torch.randn(3, H, W, generator=torch.Generator().manual_seed(2)).to(dev)
+    host = fbr._host_state(dev)
+    host.hints.pop((P, W, H), None)
+    (c0, r0), g0 = _fwd_bwd(rs, g, cot)             # first frame of this size: exact two-phase path
+    assert (P, W, H) in host.hints
+    (c1, r1), g1 = _fwd_bwd(rs, g, cot)             # second frame: speculative one-phase path, no host wait
+    assert torch.equal(c0.view(torch.int32), c1.view(torch.int32)) and torch.equal(r0, r1)
+    for k in g0:
+        assert rel_err_stats(g1[k], g0[k])[0] <= 1e-4, k
+    R = fbr.last_num_rendered(dev)
+    assert R > 1000
+    # force an overflow: pretend earlier frames of this size were almost empty
+    host.hints[(P, W, H)] = R // 2
+    with pytest.raises(fbr.BinningOverflow):
+        _fwd_bwd(rs, g, cot)                        # raised before the overflowed frame's backward is launched
+    assert host.hints[(P, W, H)] >= R                # the count that overflowed sized the next frame
+    (c2, r2), g2 = _fwd_bwd(rs, g, cot)
+    assert torch.equal(c0.view(torch.int32), c2.view(torch.int32))
+    # an overflow nobody differentiates is reported by the next call on this thread
+    host.hints[(P, W, H)] = R // 2
+    with torch.no_grad():
+        fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=g["shs"],
+                                  scales=g["scales"], rotations=g["rotations"])
+    torch.cuda.synchronize(dev)
+    with pytest.raises(fbr.BinningOverflow):
+        with torch.no_grad():
+            fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=g["shs"],
+                                      scales=g["scales"], rotations=g["rotations"])
+    torch.cuda.synchronize(dev)
+    host.pending.clear(); host.overflowed.clear()
+
+
+def test_visible_face_lookup_equals_mask_tensor(cuda_device):
+    dev = cuda_device
+    W, H, P = 320, 200, 40_000
+    cam = scenes.make_camera(W, H, device=dev)
+    params, mesh = scenes.frosting_layer(P, cam, 3, n_faces_target=6000, device=dev, view_distance=4.5)
+    a = scenes.frosting_attributes(params, mesh)
+    # 500 background Gaussians behind the mesh-bound ones: they always render (frosting_model.py:1573-1576)
+    nbg = 500
+    bgg = scenes.random_gaussians(nbg, cam, 8, device=dev)
+    a = {k: torch.cat([a[k], bgg[k]]).contiguous() for k in KEYS}
+    rs = scenes.settings_for(cam, 3, device=dev)
+    _, fv, _ = fb.rasterize_mesh(mesh["verts"], mesh["faces"], cam.full_proj_transform, H, W, mark_last_on_bg=True)
+    mask = fb.gaussian_render_mask(fv, mesh["cells"], P + nbg)
+    assert int(mask[P:].sum()) == nbg and 0 < int(mask[:P].sum()) < P
+    cot = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+    (c1, r1), g1 = _fwd_bwd(rs, a, cot, visibility_mask=mask)
+    (c2, r2), g2 = _fwd_bwd(rs, a, cot, face_visibility=(fv, mesh["cells"]))
+    assert torch.equal(c1.view(torch.int32), c2.view(torch.int32)) and torch.equal(r1, r2)
+    for k in g1:
+        assert rel_err_stats(g2[k], g1[k])[0] <= 1e-4, k
+    # the fused attribute kernel takes the same marks
+    a1 = fb.frosting_attributes_fused(params, mesh, mask[:P])
+    a2 = fb.frosting_attributes_fused(params, mesh, face_visible=fv)
+    for k in a1:
+        assert torch.equal(a1[k], a2[k]), k
+
+
+def test_views_at_odd_storage_offsets_are_accepted(cuda_device):
+    """A contiguous view whose storage offset is not a multiple of 4 floats is legal for the reference (scalar
+    loads); the shim copies it to an aligned allocation instead of faulting in a 128-bit load."""
+    dev = cuda_device
+    P, W, H = 5_000, 160, 96
+    cam, g, rs = scene(P, W, H, 4, 3, dev)
+    flat = torch.zeros(3 + 4 * P, device=dev)
+    flat[3:] = g["rotations"].reshape(-1)
+    rot_view = flat[3:].view(P, 4)
+    assert rot_view.is_contiguous() and rot_view.data_ptr() % 16 != 0
+    flat_sh = torch.zeros(1 + 48 * P, device=dev)
+    flat_sh[1:] = g["shs"].reshape(-1)
+    sh_view = flat_sh[1:].view(P, 16, 3)
+    with torch.no_grad():
+        c_ref, r_ref = fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"],
+                                                 shs=g["shs"], scales=g["scales"], rotations=g["rotations"])
+        c, r = fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=sh_view,
+                                         scales=g["scales"], rotations=rot_view)
+    assert torch.equal(c.view(torch.int32), c_ref.view(torch.int32)) and torch.equal(r, r_ref)
+
+
+def test_two_host_threads_share_a_device(cuda_device):
+    """Host state (capacity hints, status mailboxes, pending frames) is per thread: two threads rendering different
+    problem sizes on one GPU, each on its own stream, get what a single thread gets."""
+    dev = cuda_device
+    cfgs = [(30_000, 256, 160, 1), (45_000, 320, 208, 2)]
+    expect, got, errs = {}, {}, []
+    for i, (P, W, H, seed) in enumerate(cfgs):
+        cam, g, rs = scene(P, W, H, seed, 2, dev)
+        with torch.no_grad():
+            expect[i] = fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"],
+                                                  shs=g["shs"], scales=g["scales"], rotations=g["rotations"])[0].clone()
+    torch.cuda.synchronize(dev)
+
+    def work(i):
+        try:
+            P, W, H, seed = cfgs[i]
+            torch.cuda.set_device(dev)
+            cam, g, rs = scene(P, W, H, seed, 2, dev)
+            with torch.cuda.stream(torch.cuda.Stream(dev)), torch.no_grad():
+                for _ in range(6):
+                    c = fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"],
+                                                  shs=g["shs"], scales=g["scales"], rotations=g["rotations"])[0]
+                torch.cuda.current_stream(dev).synchronize()
+                got[i] = c.clone()
+        except Exception as ex:   # surfaced below
+            errs.append(repr(ex))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        assert torch.equal(got[i].view(torch.int32), expect[i].view(torch.int32))
+
+
+def test_alpha_output(cuda_device):
+    dev = cuda_device
+    P, W, H = 20_000, 200, 120
+    cam, g, rs = scene(P, W, H, 6, 1, dev)
+    with torch.no_grad():
+        color, radii, alpha = fb.GaussianRasterizer(rs)(
+            means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=g["shs"], scales=g["scales"],
+            rotations=g["rotations"], return_alpha=True)
+        # the differentiable route: one extra channel of ones, background 0 -> sum alpha_i T_i = 1 - final_T
+        _, _, ones_img = fb.GaussianRasterizer(rs)(
+            means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=g["shs"], scales=g["scales"],
+            rotations=g["rotations"], extra_features=torch.ones(P, 1, device=dev))
+    st = fb.forward_with_state(rs, g["means3D"], g["opacities"], shs=g["shs"], scales=g["scales"], rotations=g["rotations"])
+    assert alpha.shape == (H, W) and torch.equal(alpha, 1.0 - st["final_T"])
+    assert (alpha - ones_img[0]).abs().max().item() <= 2e-5
+    assert 0.0 <= float(alpha.min()) and float(alpha.max()) <= 1.0
