@@ -66,14 +66,14 @@ class Workspace(C.Structure):
 class Grads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dopacity", "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh",
-        "d_dL_dscales", "d_dL_drotations")]
+        "d_dL_dscales", "d_dL_drotations")] + [("sparse_rows", C.c_int32)]
 
 
 class FrostingParams(C.Structure):
     _fields_ = [("P", C.c_int32), ("n_verts", C.c_int32), ("n_faces", C.c_int32), ("sh_rest", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("d_bary_logits", "d_cells", "d_faces", "d_inner_verts", "d_outer_verts",
                                           "d_opacity_logits", "d_log_scales", "d_quats", "d_sh_dc", "d_sh_rest",
-                                          "d_mask", "d_face_visible")]
+                                          "d_mask", "d_face_visible", "d_radii")]
 
 
 class FrostingGrads(C.Structure):

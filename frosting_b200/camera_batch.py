@@ -139,7 +139,8 @@ class CameraBatch:
     """One rank's frames over its camera block.
 
     mode   "raster"    inputs are the rasterizer's own tensors (the a1-a19 path): mask -> forward -> loss -> backward
-           "frosting"  the frame starts from Frosting's learnable parameters (rows a20 / f1)
+           "frosting"  the frame starts from Frosting's learnable parameters (rows a20 / f1); with mask="lookup" this is
+                       the single fused op `frosting_render` (sparse-row gradient contract), else attributes + rasterizer
     mask   "lookup"    occlusion culling looked up inside preprocess from the visible-face marks (`face_visibility=`): no
                        mask tensor, no mask kernel (row f1)
            "fused"     a per-Gaussian mask tensor consumed inside preprocess (`visibility_mask=`, row a19)
@@ -179,6 +180,16 @@ class CameraBatch:
         lookup = self.mask_mode == "lookup" and self.wl["face_visible"] is not None
         mask = None if lookup else self.render_mask(i)
         fv = self.wl["face_visible"][i] if lookup else None
+        if self.mode == "frosting" and (lookup or self.wl["face_visible"] is None):
+            if self.opt is None:
+                for v in self.params.values():
+                    v.grad = None
+            color, radii = fb.frosting_render(self.params, self.wl["mesh"], rs, face_visible=fv,
+                                              grad_sink=self.opt.grads if self.opt is not None else None)
+            loss = fb.l1_dssim_loss(color, self.gt[i], 0.2) if self.loss_mode == "l1_dssim" else (color * cot).sum()
+            loss.backward()
+            self.last = dict(color=color, radii=radii, means2D=None)
+            return loss.detach()
         if self.mode == "raster":
             L = self.leaves
             for v in L.values():

@@ -127,8 +127,12 @@ frosting_attr_bwd_kernel(AttrBwdArgs a) {
     const int g0 = idx - lane;
     const bool full_warp = g0 + 31 < P;
     const bool in_range = idx < P;
-    const bool live = in_range && !(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0) &&
-                      !(a.p.d_face_visible != nullptr && a.p.d_face_visible[a.p.d_cells[idx]] == 0);
+    // with d_radii the test is "was rendered": upstream rows of unrendered Gaussians are zero by definition and may be
+    // unwritten (fb200_grads.sparse_rows), so they are not read
+    const bool live = in_range && (a.p.d_radii != nullptr
+        ? a.p.d_radii[idx] > 0
+        : (!(a.p.d_mask != nullptr && a.p.d_mask[idx] == 0) &&
+           !(a.p.d_face_visible != nullptr && a.p.d_face_visible[a.p.d_cells[idx]] == 0)));
     const unsigned live_mask = __ballot_sync(full, live);
     const size_t i = (size_t)(in_range ? idx : 0);
     float* srow = stage[warp];

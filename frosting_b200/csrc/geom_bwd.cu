@@ -73,6 +73,7 @@ geom_bwd_kernel(BwdArgs a) {
     // Frosting layer, where visibility is coherent in face order) only have zeros to write: do it with
     // fully coalesced 128-bit stores instead of 32 scattered scalar stores per thread.
     if (full_warp && !__any_sync(0xffffffffu, visible)) {
+        if (a.g.sparse_rows) return;      // the consumer knows radii: rows of unrendered Gaussians are never read (row f1)
         const size_t g = (size_t)g0;
         warp_zero4(a.g.d_dL_dmeans2D + 3 * g, 24, lane);
         if (a.g.d_dL_dcolors) warp_zero4(a.g.d_dL_dcolors + 3 * g, 24, lane);

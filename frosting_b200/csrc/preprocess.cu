@@ -220,9 +220,15 @@ preprocess_fwd_kernel(FwdArgs a) {
     const float* __restrict__ v = cam.view;
     const float* __restrict__ m = cam.proj;
 
+    // the occlusion inputs first: the cell -> visible-face gather is a dependent chain of its own, started before the
+    // position loads so that the two chains overlap (a culled Gaussian then costs two memory round trips, not three)
+    const bool by_face = a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points;
+    const long long cell = by_face ? __ldg(a.in.d_point_cells + idx) : 0;
+    const uint8_t vis_in = a.in.d_visibility != nullptr ? __ldg(a.in.d_visibility + idx) : (uint8_t)1;
     const float px = __ldg(a.in.d_means3D + 3 * (size_t)idx + 0);
     const float py = __ldg(a.in.d_means3D + 3 * (size_t)idx + 1);
     const float pz = __ldg(a.in.d_means3D + 3 * (size_t)idx + 2);
+    const uint8_t face_in = by_face ? __ldg(a.in.d_face_visible + cell) : (uint8_t)1;
 
     // in_frustum: keep iff !(p_view.z <= 0.2f)
     const float depth = affine_row(v, 2, px, py, pz);
@@ -231,11 +237,9 @@ preprocess_fwd_kernel(FwdArgs a) {
         printf("Point is filtered although prefiltered is set. This shouldn't happen!");
         __trap();
     }
-    if (a.in.d_visibility != nullptr && a.in.d_visibility[idx] == 0) keep = false;
-    // occlusion culling without a mask tensor: render_mask = face_visible[_point_cell_indices] for the mesh-bound
-    // Gaussians, True for the trailing background ones (frosting_model.py:1564-1576), looked up in place
-    if (a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points &&
-        a.in.d_face_visible[a.in.d_point_cells[idx]] == 0) keep = false;
+    // occlusion culling: a per-Gaussian mask tensor, or -- without one -- render_mask = face_visible[_point_cell_indices]
+    // for the mesh-bound Gaussians, True for the trailing background ones (frosting_model.py:1564-1576), looked up in place
+    if (vis_in == 0 || face_in == 0) keep = false;
     if (keep && a.in.d_shs != nullptr) {
         // the SH row (192 B at degree 3) is consumed last, after a chain of dependent loads; start it moving now
         const char* row = reinterpret_cast<const char*>(a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3);

@@ -171,6 +171,10 @@ typedef struct fb200_grads {
     float* d_dL_dsh;          /* [P,M,3] (may be NULL when M == 0) */
     float* d_dL_dscales;      /* [P,3]; these two may be NULL when d_cov3D_precomp is given */
     float* d_dL_drotations;   /* [P,4] */
+    int32_t sparse_rows;      /* 0: every row is written (zeros for Gaussians with radii == 0) -- the reference's dense
+                                 contract.  1 (row f1): runs of 32 Gaussians that were all not rendered are SKIPPED: their
+                                 rows stay unwritten and must not be read -- for a consumer that has d_radii and treats
+                                 radii <= 0 as a zero row (fb200_frosting_attributes_backward with d_radii) */
 } fb200_grads;
 
 int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
@@ -222,6 +226,9 @@ typedef struct fb200_frosting_params {
     const float* d_sh_rest;          /* [P,M-1,3] */
     const uint8_t* d_mask;           /* optional [P]: 0 = occluded, outputs for it are left untouched */
     const uint8_t* d_face_visible;   /* optional [F]: the same culling as face_visible[d_cells[i]] (no mask tensor) */
+    const int32_t* d_radii;          /* optional [P], backward only: a Gaussian with radii <= 0 was not rendered, its
+                                        upstream gradient rows are zero by definition and are NOT read (they may be
+                                        unwritten: fb200_grads.sparse_rows) */
 } fb200_frosting_params;
 
 typedef struct fb200_frosting_grads {      /* all fully written; inner/outer vertex gradients are accumulated */

@@ -161,3 +161,45 @@ def test_alpha_output(cuda_device):
     assert alpha.shape == (H, W) and torch.equal(alpha, 1.0 - st["final_T"])
     assert (alpha - ones_img[0]).abs().max().item() <= 2e-5
     assert 0.0 <= float(alpha.min()) and float(alpha.max()) <= 1.0
+
+
+def test_frosting_render_equals_the_two_step_path(cuda_device):
+    """Row f1: the single fused op (attribute kernel -> rasterizer with the in-kernel face lookup -> sparse-row backward ->
+    attribute backward) against the same frame built from the separate pieces (torch property chain of
+    frosting_model.py:713-799 + mask tensor + rasterizer): identical image, equal parameter gradients."""
+    dev = cuda_device
+    W, H, P = 320, 200, 50_000
+    cam = scenes.make_camera(W, H, device=dev)
+    params, mesh = scenes.frosting_layer(P, cam, 9, n_faces_target=8000, device=dev, view_distance=4.5)
+    rs = scenes.settings_for(cam, 3, device=dev)
+    _, fv, _ = fb.rasterize_mesh(mesh["verts"], mesh["faces"], cam.full_proj_transform, H, W, mark_last_on_bg=True)
+    cot = torch.randn(3, H, W, generator=torch.Generator().manual_seed(7)).to(dev)
+
+    p1 = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    m1 = dict(mesh); m1["inner"] = mesh["inner"].clone().requires_grad_(True); m1["outer"] = mesh["outer"].clone().requires_grad_(True)
+    color1, radii1 = fb.frosting_render(p1, m1, rs, face_visible=fv)
+    (color1 * cot).sum().backward()
+
+    p2 = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    m2 = dict(mesh); m2["inner"] = mesh["inner"].clone().requires_grad_(True); m2["outer"] = mesh["outer"].clone().requires_grad_(True)
+    a = scenes.frosting_attributes(p2, m2)
+    mask = fb.gaussian_render_mask(fv, mesh["cells"], P)
+    z = torch.zeros(P, 3, device=dev, requires_grad=True)
+    color2, radii2 = fb.GaussianRasterizer(rs)(means3D=a["means3D"], means2D=z, opacities=a["opacities"], shs=a["shs"],
+                                               scales=a["scales"], rotations=a["rotations"], visibility_mask=mask)
+    (color2 * cot).sum().backward()
+    assert torch.equal(radii1, radii2)
+    assert 0 < int((radii1 > 0).sum()) < P
+    # the fused attribute kernel and the torch chain agree to ~1 ulp, enough to flip a handful of alpha / rect decisions
+    d = (color1 - color2).abs()
+    assert (d > 1e-4).float().mean().item() < 1e-3 and d.max().item() < 2e-2
+    for k in p1:
+        m, frac = rel_err_stats(p1[k].grad, p2[k].grad)
+        assert m <= 2e-3, (k, m)
+    for k in ("inner", "outer"):
+        m, frac = rel_err_stats(m1[k].grad, m2[k].grad)
+        assert m <= 2e-3, (k, m)
+    # unrendered Gaussians get exact zeros although the rasterizer never wrote their rows
+    dead = radii1 <= 0
+    for k in p1:
+        assert float(p1[k].grad[dead].abs().sum()) == 0.0, k
