@@ -324,16 +324,192 @@ __device__ __forceinline__ void radix_sort_tile(u64* a, u64* b, int n,
     result = src;
 }
 
+// Stable LSD radix sort of one tile's keys by ONE warp (the fallback of the bucket sort below; round 1's sort of the
+// tiny class): same ranking as radix_sort_tile, __syncwarp only.  Returns the buffer holding the result.
+__device__ __forceinline__ u64* radix_sort_warp(u64* src, u64* dst, int n, uint32_t* cnt, int lane) {
+    const unsigned full = 0xffffffffu;
+    for (int shift = 32; shift < 64; shift += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cnt[lane + 32 * k] = 0;
+        __syncwarp();
+        // 1. digit histogram
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool have = i < n;
+            const uint32_t d = have ? (uint32_t)(src[i] >> shift) & 0xffu : 0u;
+            const unsigned peers = digit_peers(d, have);
+            if (have && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+            __syncwarp();
+        }
+        // 2. exclusive offsets: lane l owns digits 8l .. 8l+7; a digit shared by every key makes the pass an identity
+        uint32_t c[8];
+        uint32_t tot = 0;
+        bool uniform = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            c[k] = cnt[8 * lane + k];
+            uniform |= c[k] == (uint32_t)n;
+            tot += c[k];
+        }
+        if (__any_sync(full, uniform)) continue;
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t base = incl - tot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cnt[8 * lane + k] = base;
+            base += c[k];
+        }
+        __syncwarp();
+        // 3. stable scatter, 32 keys at a time in list order
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool have = i < n;
+            const u64 k = have ? src[i] : 0ull;
+            const uint32_t d = have ? (uint32_t)(k >> shift) & 0xffu : 0u;
+            const unsigned peers = digit_peers(d, have);
+            uint32_t off = 0;
+            if (have) off = cnt[d] + __popc(peers & ((1u << lane) - 1u));
+            __syncwarp();
+            if (have) {
+                dst[off] = k;
+                if ((__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        u64* t = src; src = dst; dst = t;
+    }
+    // 4. order runs of equal depth by Gaussian index (rare: exact float ties)
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t d = (uint32_t)(src[i] >> 32);
+        const bool run_start = (i == 0 || (uint32_t)(src[i - 1] >> 32) != d) && (i + 1 < n) &&
+                               (uint32_t)(src[i + 1] >> 32) == d;
+        if (run_start) {
+            int e = i + 1;
+            while (e < n && (uint32_t)(src[e] >> 32) == d) ++e;
+            for (int x = i + 1; x < e; ++x) {          // insertion sort of the run [i, e)
+                const u64 kx = src[x];
+                int y = x - 1;
+                while (y >= i && src[y] > kx) { src[y + 1] = src[y]; --y; }
+                src[y + 1] = kx;
+            }
+        }
+    }
+    __syncwarp();
+    return src;
+}
+
+// ---- bucket sort: the common case of every class --------------------------------------------------------------------
+// A tile's depths are a few hundred to a few thousand floats inside one narrow interval, close to uniform in it.  Instead
+// of four 8-bit LSD passes (two ballot-ranked sweeps each: ~10 warp-instructions per key; C5: 1.5 ms for 36 M keys), the
+// keys are dropped into kBuckets >= n equal-width buckets over the tile's own [min, max] of depth bits -- one histogram
+// sweep and one scatter sweep with native shared-memory integer atomics -- and each bucket (1-2 keys on average) is put
+// in order by an insertion sort on the full 64-bit key (depth_bits, gaussian_idx): the same total order as the
+// reference's stable sort.  A tile whose fullest bucket exceeds kInsertMax (depths piled on a few values) takes the radix
+// sort instead, decided per tile on the device.
+constexpr int kInsertMax = 24;
+
+template <int kThreads>
+__device__ __forceinline__ void scope_sync() {
+    if (kThreads == 32) __syncwarp(); else __syncthreads();
+}
+
+// Sorts a[0, n) into b[0, n); returns false (uniformly, b unspecified, a intact) when a bucket is too full.
+// cnt: kBuckets words; s_misc: words {min, max, maxcnt}; warp_tot: 32 words (CTA scope only); t: thread index in the scope.
+template <int kThreads, int kBuckets>
+__device__ __forceinline__ bool bucket_sort_tile(const u64* a, u64* b, int n, uint32_t* cnt, uint32_t* s_misc,
+                                                 uint32_t* warp_tot, int t) {
+    const unsigned full = 0xffffffffu;
+    if (t == 0) { s_misc[0] = 0xffffffffu; s_misc[1] = 0u; s_misc[2] = 0u; }
+    for (int i = t; i < kBuckets; i += kThreads) cnt[i] = 0;
+    scope_sync<kThreads>();
+    uint32_t lmin = 0xffffffffu, lmax = 0u;
+    for (int i = t; i < n; i += kThreads) {
+        const uint32_t d = (uint32_t)(a[i] >> 32);
+        lmin = min(lmin, d); lmax = max(lmax, d);
+    }
+    lmin = __reduce_min_sync(full, lmin);
+    lmax = __reduce_max_sync(full, lmax);
+    if ((t & 31) == 0) { atomicMin(&s_misc[0], lmin); atomicMax(&s_misc[1], lmax); }
+    scope_sync<kThreads>();
+    const uint32_t dmin = *(volatile uint32_t*)&s_misc[0], range = *(volatile uint32_t*)&s_misc[1] - dmin;
+    constexpr int kLog = 31 - __builtin_clz((unsigned)kBuckets);
+    const int bits = range ? 32 - __clz(range) : 0;
+    const int shift = max(0, bits - kLog);
+    // 1. histogram
+    for (int i = t; i < n; i += kThreads) atomicAdd(cnt + (((uint32_t)(a[i] >> 32) - dmin) >> shift), 1u);
+    scope_sync<kThreads>();
+    // 2. exclusive scan of the bucket counts (each thread owns kBuckets / kThreads consecutive buckets) + fullest bucket
+    constexpr int kPer = kBuckets / kThreads;
+    static_assert(kBuckets % kThreads == 0, "buckets per thread");
+    uint32_t local = 0, lmaxc = 0;
+#pragma unroll 4
+    for (int k = 0; k < kPer; ++k) {
+        const uint32_t c = cnt[t * kPer + k];
+        local += c; lmaxc = max(lmaxc, c);
+    }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(full, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    lmaxc = __reduce_max_sync(full, lmaxc);
+    uint32_t warp_base = 0;
+    if (kThreads > 32) {
+        if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+        if ((t & 31) == 0) atomicMax(&s_misc[2], lmaxc);
+        __syncthreads();
+        for (int w = 0; w < (t >> 5); ++w) warp_base += warp_tot[w];
+        lmaxc = *(volatile uint32_t*)&s_misc[2];
+    }
+    if (lmaxc > (uint32_t)kInsertMax) return false;          // uniform over the scope
+    uint32_t run = warp_base + incl - local;
+#pragma unroll 4
+    for (int k = 0; k < kPer; ++k) {
+        const uint32_t c = cnt[t * kPer + k];
+        cnt[t * kPer + k] = run;
+        run += c;
+    }
+    scope_sync<kThreads>();
+    // 3. scatter (the order inside a bucket is whatever the atomics make it; step 4 fixes it)
+    for (int i = t; i < n; i += kThreads) {
+        const u64 k = a[i];
+        b[atomicAdd(cnt + (((uint32_t)(k >> 32) - dmin) >> shift), 1u)] = k;
+    }
+    scope_sync<kThreads>();
+    // 4. insertion sort inside each bucket; cnt[j] is now the END of bucket j
+    for (int j = t; j < kBuckets; j += kThreads) {
+        const int lo = j ? (int)cnt[j - 1] : 0, hi = (int)cnt[j];
+        for (int x = lo + 1; x < hi; ++x) {
+            const u64 kx = b[x];
+            int y = x - 1;
+            while (y >= lo && b[y] > kx) { b[y + 1] = b[y]; --y; }
+            b[y + 1] = kx;
+        }
+    }
+    scope_sync<kThreads>();
+    return true;
+}
+
 template <int kThreads, int kMaxN, bool kDynamic>
 __global__ void __launch_bounds__(kThreads)
 tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
                         const uint2* __restrict__ ranges, u64* __restrict__ keys,
                         uint32_t* __restrict__ point_list, const int32_t* __restrict__ status) {
+    // counters: kMaxN bucket words for the bucket sort; their first (kThreads / 32) * 256 double as the radix fallback's
+    // per-warp digit counters
+    static_assert(kMaxN >= (kThreads / 32) * 256, "counter aliasing");
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ u64 stat_a[kDynamic ? 1 : kMaxN];
     __shared__ u64 stat_b[kDynamic ? 1 : kMaxN];
-    __shared__ uint32_t stat_counters[kDynamic ? 1 : (kThreads / 32) * 256];
-    __shared__ uint32_t s_misc[16];
+    __shared__ uint32_t stat_counters[kDynamic ? 1 : kMaxN];
+    __shared__ uint32_t s_misc[40];
+    __shared__ uint32_t s_warp_tot[32];
     u64* buf_a = kDynamic ? reinterpret_cast<u64*>(dyn_smem) : stat_a;
     u64* buf_b = kDynamic ? reinterpret_cast<u64*>(dyn_smem) + kMaxN : stat_b;
     uint32_t* counters = kDynamic ? reinterpret_cast<uint32_t*>(dyn_smem + 2 * sizeof(u64) * kMaxN) : stat_counters;
@@ -345,8 +521,11 @@ tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __res
         u64* g = keys + rg.x;
         for (int i = threadIdx.x; i < n; i += kThreads) buf_a[i] = g[i];
         __syncthreads();
-        u64* res;
-        radix_sort_tile<kThreads>(buf_a, buf_b, n, counters, s_misc, res);
+        u64* res = buf_b;
+        if (!bucket_sort_tile<kThreads, kMaxN>(buf_a, buf_b, n, counters, s_misc, s_warp_tot, threadIdx.x)) {
+            __syncthreads();
+            radix_sort_tile<kThreads>(buf_a, buf_b, n, counters, s_misc, res);
+        }
         for (int i = threadIdx.x; i < n; i += kThreads) {
             const u64 k = res[i];
             g[i] = k;
@@ -357,11 +536,9 @@ tile_sort_shared_kernel(const uint32_t* __restrict__ list, const uint32_t* __res
 }
 
 // ---- tiny lists: one WARP per tile ---------------------------------------------------------------------
-// Most tiles of a real frame hold a few hundred instances (C3: 428 on average).  Spreading such a list over the 8
-// warps of a CTA leaves each warp one or two 32-key steps per pass between seven CTA barriers -- the kernel was
-// barrier/latency bound (profiles/r01_c3_v2_summary.json: issue-active 39 %, barrier the top stall).  Here a warp
-// sorts a whole tile by itself (same stable LSD radix, same ballot ranking, __syncwarp only), so an SM runs dozens of
-// independent tile sorts and the work is throughput-bound.
+// Most tiles of a real frame hold a few hundred instances.  Spreading such a list over the 8 warps of a CTA leaves each
+// warp one or two 32-key steps per pass between CTA barriers (round 1: issue-active 39 %, barrier the top stall).  Here a
+// warp sorts a whole tile by itself (__syncwarp only), so an SM runs dozens of independent tile sorts.
 template <int kWarps>
 __global__ void __launch_bounds__(32 * kWarps)
 tile_sort_warp_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
@@ -369,12 +546,11 @@ tile_sort_warp_kernel(const uint32_t* __restrict__ list, const uint32_t* __restr
                       const int32_t* __restrict__ status) {
     __shared__ u64 s_a[kWarps][kSortTinyMax];
     __shared__ u64 s_b[kWarps][kSortTinyMax];
-    __shared__ uint32_t s_cnt[kWarps][256];
+    __shared__ uint32_t s_cnt[kWarps][kSortTinyMax];
+    __shared__ uint32_t s_misc[kWarps][4];
     if (status[FB200_ST_OVERFLOW]) return;
-    const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t count = *n_list;
-    uint32_t* cnt = s_cnt[warp];
     for (uint32_t w = blockIdx.x * kWarps + warp; w < count; w += gridDim.x * kWarps) {
         const uint2 rg = ranges[list[w]];
         const int n = (int)(rg.y - rg.x);
@@ -387,80 +563,11 @@ tile_sort_warp_kernel(const uint32_t* __restrict__ list, const uint32_t* __restr
         u64* dst = s_b[warp];
         for (int i = lane; i < n; i += 32) src[i] = g[i];
         __syncwarp();
-        for (int shift = 32; shift < 64; shift += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) cnt[lane + 32 * k] = 0;
-            __syncwarp();
-            // 1. digit histogram
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const int i = i0 + lane;
-                const bool have = i < n;
-                const uint32_t d = have ? (uint32_t)(src[i] >> shift) & 0xffu : 0u;
-                const unsigned peers = digit_peers(d, have);
-                if (have && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
-                __syncwarp();
-            }
-            // 2. exclusive offsets: lane l owns digits 8l .. 8l+7; a digit shared by every key makes the pass an identity
-            uint32_t c[8];
-            uint32_t tot = 0;
-            bool uniform = false;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                c[k] = cnt[8 * lane + k];
-                uniform |= c[k] == (uint32_t)n;
-                tot += c[k];
-            }
-            if (__any_sync(full, uniform)) continue;
-            uint32_t incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(full, incl, o);
-                if (lane >= o) incl += t;
-            }
-            uint32_t base = incl - tot;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                cnt[8 * lane + k] = base;
-                base += c[k];
-            }
-            __syncwarp();
-            // 3. stable scatter, 32 keys at a time in list order
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const int i = i0 + lane;
-                const bool have = i < n;
-                const u64 k = have ? src[i] : 0ull;
-                const uint32_t d = have ? (uint32_t)(k >> shift) & 0xffu : 0u;
-                const unsigned peers = digit_peers(d, have);
-                uint32_t off = 0;
-                if (have) off = cnt[d] + __popc(peers & ((1u << lane) - 1u));
-                __syncwarp();
-                if (have) {
-                    dst[off] = k;
-                    if ((__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
-                }
-                __syncwarp();
-            }
-            u64* t = src; src = dst; dst = t;
-        }
-        // 4. order runs of equal depth by Gaussian index (rare: exact float ties)
+        const u64* res = dst;
+        if (!bucket_sort_tile<32, kSortTinyMax>(src, dst, n, s_cnt[warp], s_misc[warp], nullptr, lane))
+            res = radix_sort_warp(src, dst, n, s_cnt[warp], lane);
         for (int i = lane; i < n; i += 32) {
-            const uint32_t d = (uint32_t)(src[i] >> 32);
-            const bool run_start = (i == 0 || (uint32_t)(src[i - 1] >> 32) != d) && (i + 1 < n) &&
-                                   (uint32_t)(src[i + 1] >> 32) == d;
-            if (run_start) {
-                int e = i + 1;
-                while (e < n && (uint32_t)(src[e] >> 32) == d) ++e;
-                for (int x = i + 1; x < e; ++x) {          // insertion sort of the run [i, e)
-                    const u64 kx = src[x];
-                    int y = x - 1;
-                    while (y >= i && src[y] > kx) { src[y + 1] = src[y]; --y; }
-                    src[y + 1] = kx;
-                }
-            }
-        }
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const u64 k = src[i];
+            const u64 k = res[i];
             g[i] = k;
             point_list[rg.x + i] = (uint32_t)k;
         }
@@ -564,7 +671,7 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
         s2 = side->stream;
     }
     {
-        constexpr int kWarps = 4;                        // 4 x 9 KB of shared memory per CTA
+        constexpr int kWarps = 4;                        // 4 x 10 KB of shared memory per CTA
         const int grid = min((T + kWarps - 1) / kWarps, 148 * 6);
         tile_sort_warp_kernel<kWarps><<<grid, 32 * kWarps, 0, s>>>(a.list_tiny, a.counters + 4, a.ranges, a.keys,
                                                                    a.point_list, a.status);
@@ -579,7 +686,7 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
     if (max_tile > kSortSmallMax) {
         // medium lists (2048 < n <= 8192): 1024 threads, ping-pong buffers + per-warp counters in 160 KB of
         // dynamic shared memory, one CTA per SM
-        const int smem = 2 * 8 * kSortMediumMax + 32 * 256 * 4;
+        const int smem = 2 * 8 * kSortMediumMax + 4 * kSortMediumMax;     // two key buffers + one counter word per bucket
         // per call, not once per process: the attribute is per device
         const cudaError_t attr = cudaFuncSetAttribute(tile_sort_shared_kernel<1024, kSortMediumMax, true>,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -414,6 +414,15 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     }
     if (top == 0) return;
     __syncwarp();
+    // Pixel-pair slot k (0..7) of phases 1 / 3 covers pixels {2k, 2k+1} of the upper half and {16+2k, 16+2k+1} of the
+    // lower half at once.  pair_last[k] = the largest "last entry" among those four pixels: a block whose entries all lie
+    // at or beyond it has nothing to do in slot k.  Deep in a list only the few pixels that never saturated are still
+    // live, so most slots are skipped there (C2 / C5: most of the walk).
+    uint32_t pair_last;
+    {
+        const int k = lane & 7;
+        pair_last = max(max(sm.last[2 * k], sm.last[2 * k + 1]), max(sm.last[16 + 2 * k], sm.last[17 + 2 * k]));
+    }
 
     // ---- lane = (Gaussian g, pixel half h): rows 2h, 2h+1 of the 8x4 sub-tile ----
     const int g = lane & (kBlk - 1), h = lane >> 4;
@@ -452,41 +461,58 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const uint32_t gid = nid;
         top -= cnt;
         fetch(top);
-        // ---- phase 1: alpha of (Gaussian g) x (16 pixels), the forward's op order ----
+        // ---- phase 1: alpha of (Gaussian g) x (up to 16 pixels), the forward's op order ----
+        // slots that can hold a contributing pixel for some entry of this block (entries [top, top + cnt) after the update)
+        const unsigned slots = __ballot_sync(full, pair_last > (uint32_t)top) & 0xffu;
         bool any_act = false;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        unsigned my_slots = 0;          // slots where THIS lane found a contributing pixel
+        auto phase1 = [&](int r, int c) {
             const float dy = fadd(Y, -(py0 + (float)r));
             const float dyC = fmul(dy, fmul(dy, Cc));
+            const int k = 8 * r + 2 * c;                                   // pixel pair (k, k+1) of this half
+            const P2 dx = add2(bc(X), p2(-(px0 + (float)(2 * c)), -(px0 + (float)(2 * c + 1))));
+            const P2 q = fma2(dx, mul2(dx, bc(A)), bc(dyC));
+            const P2 u = mul2(bc(dy), mul2(dx, bc(B)));
+            const P2 power = fma2(q, bc(-0.5f), neg2(u));
+            const P2 og = mul2(bc(op), exp_pair(power));
+            const uint2 lastp = *reinterpret_cast<const uint2*>(plast + k);
+            // contributes iff the forward blended it: not beyond the pixel's last contributor, power <= 0,
+            // alpha >= 1/255 (min(0.99, og) < 1/255  <=>  og < 1/255)
+            const bool a0 = valid && (entry < lastp.x) && !(power.x > 0.0f) && !(og.x < 1.0f / 255.0f);
+            const bool a1 = valid && (entry < lastp.y) && !(power.y > 0.0f) && !(og.y < 1.0f / 255.0f);
+            any_act |= a0 | a1;
+            my_slots |= (a0 | a1) ? (1u << (4 * r + c)) : 0u;
+            const P2 ogm = p2(a0 ? og.x : 0.f, a1 ? og.y : 0.f);
+            const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
+            const P2 om = add2(bc(1.0f), neg2(am));                        // 1 - alpha in [0.01, 1]
+            P2 inv;
+            {
+                float i0, i1;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(om.x));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(om.y));
+                const P2 rr = p2(i0, i1);
+                inv = fma2(rr, fma2(neg2(om), rr, bc(1.0f)), rr);          // one Newton step
+            }
+            const P2 cd = fma2(ldp(pdp0, k), bc(cr), fma2(ldp(pdp1, k), bc(cg), mul2(ldp(pdp2, k), bc(cb))));
+            *reinterpret_cast<float2*>(row0 + k) = ogm;
+            *reinterpret_cast<float2*>(row1 + k) = inv;
+            *reinterpret_cast<float2*>(row2 + k) = mul2(am, cd);
+        };
+        if (slots == 0xffu) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int k = 8 * r + 2 * c;                                   // pixel pair (k, k+1) of this half
-                const P2 dx = add2(bc(X), p2(-(px0 + (float)(2 * c)), -(px0 + (float)(2 * c + 1))));
-                const P2 q = fma2(dx, mul2(dx, bc(A)), bc(dyC));
-                const P2 u = mul2(bc(dy), mul2(dx, bc(B)));
-                const P2 power = fma2(q, bc(-0.5f), neg2(u));
-                const P2 og = mul2(bc(op), exp_pair(power));
-                const uint2 lastp = *reinterpret_cast<const uint2*>(plast + k);
-                // contributes iff the forward blended it: not beyond the pixel's last contributor, power <= 0,
-                // alpha >= 1/255 (min(0.99, og) < 1/255  <=>  og < 1/255)
-                const bool a0 = valid && (entry < lastp.x) && !(power.x > 0.0f) && !(og.x < 1.0f / 255.0f);
-                const bool a1 = valid && (entry < lastp.y) && !(power.y > 0.0f) && !(og.y < 1.0f / 255.0f);
-                any_act |= a0 | a1;
-                const P2 ogm = p2(a0 ? og.x : 0.f, a1 ? og.y : 0.f);
-                const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
-                const P2 om = add2(bc(1.0f), neg2(am));                        // 1 - alpha in [0.01, 1]
-                P2 inv;
-                {
-                    float i0, i1;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(om.x));
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(om.y));
-                    const P2 rr = p2(i0, i1);
-                    inv = fma2(rr, fma2(neg2(om), rr, bc(1.0f)), rr);          // one Newton step
-                }
-                const P2 cd = fma2(ldp(pdp0, k), bc(cr), fma2(ldp(pdp1, k), bc(cg), mul2(ldp(pdp2, k), bc(cb))));
-                *reinterpret_cast<float2*>(row0 + k) = ogm;
-                *reinterpret_cast<float2*>(row1 + k) = inv;
-                *reinterpret_cast<float2*>(row2 + k) = mul2(am, cd);
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) phase1(r, c);
+        } else {
+            // skipped slots keep whatever an earlier block left in the matrices: make them identities for phase 2
+            for (unsigned todo = ~slots & 0xffu; todo; todo &= todo - 1) {
+                const int sl = __ffs(todo) - 1, k = 8 * (sl >> 2) + 2 * (sl & 3);
+                *reinterpret_cast<float2*>(row1 + k) = make_float2(1.f, 1.f);
+                *reinterpret_cast<float2*>(row2 + k) = make_float2(0.f, 0.f);
+            }
+            for (unsigned todo = slots; todo; todo &= todo - 1) {
+                const int sl = __ffs(todo) - 1;
+                phase1(sl >> 2, sl & 3);
             }
         }
         // Gaussians of the block with at least one contributing pixel (either half); the others are identities for the
@@ -527,27 +553,36 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const float rop = op > 0.f ? __frcp_rn(op) : 0.f;
         P2 sR = bc(0.f), sG = bc(0.f), sB = bc(0.f), sO = bc(0.f);
         P2 M10 = bc(0.f), M01 = bc(0.f), M20 = bc(0.f), M11 = bc(0.f), M02 = bc(0.f);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        auto phase3 = [&](int r, int c) {
             const float dy = fadd(Y, -(py0 + (float)r));
+            const int k = 8 * r + 2 * c;
+            const P2 dx = add2(bc(X), p2(-(px0 + (float)(2 * c)), -(px0 + (float)(2 * c + 1))));
+            const P2 ogm = ldp(row0, k), Tg = ldp(row1, k), U = ldp(row2, k);
+            const P2 d0 = ldp(pdp0, k), d1 = ldp(pdp1, k), d2 = ldp(pdp2, k);
+            const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
+            const P2 Gm = mul2(ogm, bc(rop));                               // G (0 where the pair does not contribute)
+            const P2 cd = fma2(d0, bc(cr), fma2(d1, bc(cg), mul2(d2, bc(cb))));
+            const P2 dch = mul2(am, Tg);                                   // d(pixel channel)/d(colour)
+            sR = fma2(dch, d0, sR); sG = fma2(dch, d1, sG); sB = fma2(dch, d2, sB);
+            const P2 dLa = fma2(Tg, cd, U);                                // dL/dalpha
+            const P2 S = mul2(dLa, Gm);                                    // dL/dopacity contribution
+            sO = add2(sO, S);
+            const P2 SG = mul2(S, bc(op));                                 // dL/dG * G
+            const P2 sx = mul2(SG, dx), sy = mul2(SG, bc(dy));
+            M10 = add2(M10, sx); M01 = add2(M01, sy);
+            M20 = fma2(sx, dx, M20); M11 = fma2(sx, bc(dy), M11); M02 = fma2(sy, bc(dy), M02);
+        };
+        // only the slots where some lane found a contributing pixel carry anything
+        const unsigned live_slots = __reduce_or_sync(full, my_slots);
+        if (live_slots == 0xffu) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int k = 8 * r + 2 * c;
-                const P2 dx = add2(bc(X), p2(-(px0 + (float)(2 * c)), -(px0 + (float)(2 * c + 1))));
-                const P2 ogm = ldp(row0, k), Tg = ldp(row1, k), U = ldp(row2, k);
-                const P2 d0 = ldp(pdp0, k), d1 = ldp(pdp1, k), d2 = ldp(pdp2, k);
-                const P2 am = p2(fminf(0.99f, ogm.x), fminf(0.99f, ogm.y));
-                const P2 Gm = mul2(ogm, bc(rop));                               // G (0 where the pair does not contribute)
-                const P2 cd = fma2(d0, bc(cr), fma2(d1, bc(cg), mul2(d2, bc(cb))));
-                const P2 dch = mul2(am, Tg);                                   // d(pixel channel)/d(colour)
-                sR = fma2(dch, d0, sR); sG = fma2(dch, d1, sG); sB = fma2(dch, d2, sB);
-                const P2 dLa = fma2(Tg, cd, U);                                // dL/dalpha
-                const P2 S = mul2(dLa, Gm);                                    // dL/dopacity contribution
-                sO = add2(sO, S);
-                const P2 SG = mul2(S, bc(op));                                 // dL/dG * G
-                const P2 sx = mul2(SG, dx), sy = mul2(SG, bc(dy));
-                M10 = add2(M10, sx); M01 = add2(M01, sy);
-                M20 = fma2(sx, dx, M20); M11 = fma2(sx, bc(dy), M11); M02 = fma2(sy, bc(dy), M02);
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) phase3(r, c);
+        } else {
+            for (unsigned todo = live_slots; todo; todo &= todo - 1) {
+                const int sl = __ffs(todo) - 1;
+                phase3(sl >> 2, sl & 3);
             }
         }
         float v[9] = {M10.x + M10.y, M01.x + M01.y, M20.x + M20.y, M11.x + M11.y, M02.x + M02.y,
