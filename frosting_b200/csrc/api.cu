@@ -335,8 +335,20 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
 
     if (!ws->acc_zeroed_by_forward &&
         (rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
+    // the zero rows of the dense-gradient contract are written on a side stream while the blend backward runs
+    SideStream* side = (!grads->sparse_rows && !debug && prm->P >= 4096) ? side_stream() : nullptr;
+    std::unique_lock<std::mutex> side_use;
+    if (side) {
+        side_use = std::unique_lock<std::mutex>(side->use);
+        if ((rc = check(cudaEventRecord(side->fork, s), "fork")) != FB200_OK) return rc;
+        if ((rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork")) != FB200_OK) return rc;
+        if ((rc = check(launch_zero_rows(a, side->stream), "zero rows")) != FB200_OK) return rc;
+        if ((rc = check(cudaEventRecord(side->join, side->stream), "join")) != FB200_OK) return rc;
+        a.zeroed_elsewhere = 1;
+    }
     { StageTimer t(FB200_STAGE_RENDER_BWD, s);
       if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc; }
+    if (side && (rc = check(cudaStreamWaitEvent(s, side->join, 0), "join")) != FB200_OK) return rc;
     { StageTimer t(FB200_STAGE_GEOM_BWD, s);
       if ((rc = stage(launch_geom_bwd(a, s), "geometry backward", debug, s)) != FB200_OK) return rc; }
     if ((rc = stage(launch_extra_grad(a, s), "extra feature gradients", debug, s)) != FB200_OK) return rc;

@@ -619,14 +619,7 @@ __global__ void check_capacity_kernel(long long capacity, int32_t* __restrict__ 
 
 // The tiny-list and small-list sorts are independent and each ends in a long tail (a few long lists on a few SMs);
 // the small-list kernel therefore runs on a side stream, forked after the scatter and joined before the blend.
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    bool ready = false;
-    std::mutex use;     // one fork ... join sequence at a time: the two events are re-recorded by every caller
-};
-
-static SideStream* side_stream() {
+SideStream* side_stream() {
     static SideStream pool[64];
     static std::mutex mu;
     int dev = 0;

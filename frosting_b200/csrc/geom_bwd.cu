@@ -50,6 +50,36 @@ __device__ __forceinline__ void warp_zero4(float* base, int n4, int lane) {
     for (int i = lane; i < n4; i += 32) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// all gradient rows of the 32 Gaussians starting at g: fully coalesced 128-bit zero stores
+__device__ __forceinline__ void zero_warp_rows(const BwdArgs& a, size_t g, int M, int lane) {
+    warp_zero4(a.g.d_dL_dmeans2D + 3 * g, 24, lane);
+    if (a.g.d_dL_dcolors) warp_zero4(a.g.d_dL_dcolors + 3 * g, 24, lane);
+    warp_zero4(a.g.d_dL_dopacity + g, 8, lane);
+    warp_zero4(a.g.d_dL_dmeans3D + 3 * g, 24, lane);
+    if (a.g.d_dL_dcov3D) warp_zero4(a.g.d_dL_dcov3D + 6 * g, 48, lane);
+    if (a.g.d_dL_dscales) warp_zero4(a.g.d_dL_dscales + 3 * g, 24, lane);
+    if (a.g.d_dL_drotations) warp_zero4(a.g.d_dL_drotations + 4 * g, 32, lane);
+    if (a.g.d_dL_dsh != nullptr && M > 0 && ((M * 3) & 3) == 0) warp_zero4(a.g.d_dL_dsh + (size_t)M * 3 * g, M * 24, lane);
+    else if (a.g.d_dL_dsh != nullptr && M > 0)
+        for (int k = lane; k < M * 3 * 32; k += 32) a.g.d_dL_dsh[(size_t)M * 3 * g + k] = 0.f;
+}
+
+// The dense-gradient contract of the reference (zeros for every Gaussian that was not rendered: 300 B each, 540 MB of
+// stores at C3) is pure HBM traffic with no dependence on the blend backward, which is issue-bound and leaves HBM idle
+// (3 % of peak): this kernel writes those zero rows on a side stream WHILE the blend backward runs; geom_bwd_kernel then
+// only handles the warps with something to compute.
+__global__ void __launch_bounds__(256)
+zero_rows_kernel(BwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int P = a.prm.P, M = a.prm.sh_coeffs;
+    for (long long g0 = warp_id * 32; g0 + 31 < P; g0 += n_warps * 32) {
+        const bool visible = a.radii[g0 + lane] > 0;
+        if (!__any_sync(0xffffffffu, visible)) zero_warp_rows(a, (size_t)g0, M, lane);
+    }
+}
+
 __global__ void __launch_bounds__(kGeomThreads)
 geom_bwd_kernel(BwdArgs a) {
     __shared__ float view[16], proj[16], campos[3];
@@ -73,18 +103,10 @@ geom_bwd_kernel(BwdArgs a) {
     // Frosting layer, where visibility is coherent in face order) only have zeros to write: do it with
     // fully coalesced 128-bit stores instead of 32 scattered scalar stores per thread.
     if (full_warp && !__any_sync(0xffffffffu, visible)) {
-        if (a.g.sparse_rows) return;      // the consumer knows radii: rows of unrendered Gaussians are never read (row f1)
-        const size_t g = (size_t)g0;
-        warp_zero4(a.g.d_dL_dmeans2D + 3 * g, 24, lane);
-        if (a.g.d_dL_dcolors) warp_zero4(a.g.d_dL_dcolors + 3 * g, 24, lane);
-        warp_zero4(a.g.d_dL_dopacity + g, 8, lane);
-        warp_zero4(a.g.d_dL_dmeans3D + 3 * g, 24, lane);
-        if (a.g.d_dL_dcov3D) warp_zero4(a.g.d_dL_dcov3D + 6 * g, 48, lane);
-        if (a.g.d_dL_dscales) warp_zero4(a.g.d_dL_dscales + 3 * g, 24, lane);
-        if (a.g.d_dL_drotations) warp_zero4(a.g.d_dL_drotations + 4 * g, 32, lane);
-        if (a.g.d_dL_dsh != nullptr && M > 0 && ((M * 3) & 3) == 0) warp_zero4(a.g.d_dL_dsh + (size_t)M * 3 * g, M * 24, lane);
-        else if (a.g.d_dL_dsh != nullptr && M > 0)
-            for (int k = lane; k < M * 3 * 32; k += 32) a.g.d_dL_dsh[(size_t)M * 3 * g + k] = 0.f;
+        // sparse_rows: the consumer knows radii and never reads these rows (row f1); zero_elsewhere: zero_rows_kernel has
+        // written them, concurrently with the blend backward
+        if (a.g.sparse_rows || a.zeroed_elsewhere) return;
+        zero_warp_rows(a, (size_t)g0, M, lane);
         return;
     }
     const size_t i = (size_t)(in_range ? idx : 0);
@@ -352,6 +374,14 @@ geom_bwd_kernel(BwdArgs a) {
 }
 
 }  // namespace
+
+cudaError_t launch_zero_rows(const BwdArgs& a, cudaStream_t s) {
+    if (a.prm.P >= 32) {
+        zero_rows_kernel<<<148 * 8, 256, 0, s>>>(a);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_geom_bwd(const BwdArgs& a, cudaStream_t s) {
     if (a.prm.P > 0) {
