@@ -489,6 +489,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(cb.WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="developer runs: headline + stage profile only")
+    ap.add_argument("--with-dp", action="store_true", help="with --quick: also run the data-parallel training leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: route fd 1 to stderr for the whole run (NCCL / C libraries print their
@@ -616,7 +617,10 @@ def main():
 
     # ---- the data-parallel TRAINING iteration (row f3).  It is the only leg that maps memory across ranks; it runs under
     # a watchdog, so a stuck rendezvous cannot take the line down
-    if wl.get("params") is not None and not args.quick:
+    if wl.get("params") is not None and (not args.quick or args.with_dp):
+        if gts is None:
+            gtg = torch.Generator().manual_seed(99 + rank)
+            gts = [torch.rand(3, H, W, generator=gtg).to(device) for _ in wl["cams"]]
         lock, finished = threading.Lock(), [False]
 
         def bail():

@@ -336,7 +336,7 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     if (!ws->acc_zeroed_by_forward &&
         (rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
     // the zero rows of the dense-gradient contract are written on a side stream while the blend backward runs
-    SideStream* side = (!grads->sparse_rows && !debug && prm->P >= 4096) ? side_stream() : nullptr;
+    SideStream* side = (!grads->sparse_rows && !debug && !(prm->debug & 32) && prm->P >= 4096) ? side_stream() : nullptr;
     std::unique_lock<std::mutex> side_use;
     if (side) {
         side_use = std::unique_lock<std::mutex>(side->use);

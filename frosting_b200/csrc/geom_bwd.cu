@@ -68,7 +68,7 @@ __device__ __forceinline__ void zero_warp_rows(const BwdArgs& a, size_t g, int M
 // stores at C3) is pure HBM traffic with no dependence on the blend backward, which is issue-bound and leaves HBM idle
 // (3 % of peak): this kernel writes those zero rows on a side stream WHILE the blend backward runs; geom_bwd_kernel then
 // only handles the warps with something to compute.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 zero_rows_kernel(BwdArgs a) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -377,7 +377,8 @@ geom_bwd_kernel(BwdArgs a) {
 
 cudaError_t launch_zero_rows(const BwdArgs& a, cudaStream_t s) {
     if (a.prm.P >= 32) {
-        zero_rows_kernel<<<148 * 8, 256, 0, s>>>(a);
+        // HBM-bound stores: one small CTA per SM keeps HBM busy without taking the blend backward's warp slots
+        zero_rows_kernel<<<148, 128, 0, s>>>(a);
         count_launch();
     }
     return cudaGetLastError();

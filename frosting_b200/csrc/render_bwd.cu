@@ -354,7 +354,6 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 // bank-conflict free.
 constexpr int kBlk = 16;            // Gaussians per block
 constexpr int kRow = 34;            // padded row length (floats) of the [kBlk][32 pixels] matrices
-constexpr int kStages = 4;          // record ring: a block's records are requested kStages - 1 blocks before they are used
 
 struct __align__(16) BwdWarpSmem {
     float m0[kBlk * kRow];          // masked opacity * G                       (phase 1 -> phase 3)
@@ -362,8 +361,6 @@ struct __align__(16) BwdWarpSmem {
     float m2[kBlk * kRow];          // alpha * (c . dL/dpix)  -> U              (phase 1 -> 2 -> 3)
     float dp0[32], dp1[32], dp2[32], K[32];     // per pixel: dL/dpixel, K = -T_final * (bg . dL/dpixel)
     uint32_t last[32];                          // per pixel: entries of the hit list up to its last contributor
-    SplatRec ring[kStages][kBlk];               // records of the blocks in flight (cp.async.bulk destinations)
-    uint64_t bar[kStages];                      // one mbarrier per ring stage
 };
 
 // The list a warp walks is its sub-tile's HIT LIST, written by the forward blend (render_fwd.cu): the Gaussian ids
@@ -440,63 +437,33 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const float* const pdp2 = sm.dp2 + 16 * h;
     const uint32_t* const plast = sm.last + 16 * h;
 
-    // ---- record staging: TMA gather into a shared-memory ring ---------------------------------------------------------
-    // Block b (b = 0 at the deep end) covers entries [e_hi - 16 b - cnt, e_hi - 16 b).  Its 16 records are scattered in
-    // the per-Gaussian array, so each of the 16 owning lanes issues ONE 48-byte cp.async.bulk into its slot of ring stage
-    // b % kStages; the copies complete on the stage's mbarrier.  They are issued kStages - 1 blocks ahead (their ids one
-    // block earlier still), with no register cost, so that the cheap blocks of a sparse tail -- a few hundred cycles each --
-    // do not wait for two dependent L2 round trips (round-2 v5 profile at C2: issue-active 28 %, long-scoreboard the top
-    // stall; profiles/r02_bwd_blend.md).
-    const int e_hi = top;
-    const int nblk = (e_hi + kBlk - 1) / kBlk;
-    if (lane == 0) {
-#pragma unroll
-        for (int st = 0; st < kStages; ++st) mbar_init(&sm.bar[st], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    auto load_id = [&](int b) -> uint32_t {
-        const int e = e_hi - kBlk * b - 1 - g;
-        return (b < nblk && e >= 0) ? __ldg(sub + e) : 0u;
-    };
-    auto issue = [&](int b, uint32_t id) {
-        if (b >= nblk) return;
-        const int st = b % kStages;
-        const int c = min(kBlk, e_hi - kBlk * b);
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage's previous readers are done
-            mbar_expect_tx(&sm.bar[st], (uint32_t)c * (uint32_t)sizeof(SplatRec));
+    // The next block's records are fetched into registers while the current block is processed (one dependent hop:
+    // id -> record).  A/B (profiles/r02_tma_ab.md): staging them with one 48-byte cp.async.bulk per record into a 4-deep
+    // shared-memory ring, 3 blocks ahead, was SLOWER (C3: 0.408 vs 0.337 ms) -- 16 small bulk copies per block per warp
+    // exceed what the SM's TMA unit issues, and the warps spin on the mbarriers.
+    uint32_t nid = 0;
+    float4 n0, n1, n2;
+    n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int t) {       // entries t-1 ... t-16 (lane g takes entry t-1-g)
+        const int e = t - 1 - g;
+        if (e >= 0) {
+            nid = sub[e];
+            const float4* p = reinterpret_cast<const float4*>(rec + nid);
+            n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2);
         }
-        __syncwarp();
-        if (h == 0 && g < c) bulk_g2s(&sm.ring[st][g], rec + id, (uint32_t)sizeof(SplatRec), &sm.bar[st]);
     };
-    uint32_t id_q;                  // ids of the block that is issued next
-    {
-        uint32_t ids[kStages];
-#pragma unroll
-        for (int b = 0; b < kStages; ++b) ids[b] = load_id(b);
-#pragma unroll
-        for (int b = 0; b < kStages - 1; ++b) issue(b, ids[b]);
-        id_q = ids[kStages - 1];
-    }
+    fetch(top);
 
-    for (int blk = 0; blk < nblk; ++blk) {
+    while (top > 0) {
         const int cnt = min(kBlk, top);
         const bool valid = g < cnt;
         const uint32_t entry = (uint32_t)(top - 1 - g);          // this Gaussian's entry number (valid lanes)
-        const uint32_t gid = valid ? __ldg(sub + entry) : 0u;    // (an L1/L2 hit: fetched as id_q a few blocks ago)
-        top -= cnt;
-        {
-            const uint32_t id_new = load_id(blk + kStages);
-            issue(blk + kStages - 1, id_q);
-            id_q = id_new;
-        }
-        mbar_wait(&sm.bar[blk % kStages], (uint32_t)((blk / kStages) & 1));
-        const float4* rp = reinterpret_cast<const float4*>(&sm.ring[blk % kStages][g]);
-        const float4 n0 = rp[0], n1 = rp[1], n2 = rp[2];
         const float X = n0.x, Y = n0.y, A = n0.z, B = n0.w, Cc = n1.x;
         const float op = valid ? n1.y : 0.f;
         const float cr = valid ? n1.z : 0.f, cg = valid ? n1.w : 0.f, cb = valid ? n2.x : 0.f;
+        const uint32_t gid = nid;
+        top -= cnt;
+        fetch(top);
         // ---- phase 1: alpha of (Gaussian g) x (up to 16 pixels), the forward's op order ----
         // slots that can hold a contributing pixel for some entry of this block (entries [top, top + cnt) after the update)
         const unsigned slots = __ballot_sync(full, pair_last > (uint32_t)top) & 0xffu;
