@@ -222,6 +222,7 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     a.list_small = reinterpret_cast<uint32_t*>(im + il.list_small);
     a.list_large = reinterpret_cast<uint32_t*>(im + il.list_large);
     a.list_huge = reinterpret_cast<uint32_t*>(im + il.list_huge);
+    a.tile_order = reinterpret_cast<uint32_t*>(im + il.tile_order);
     a.counters = reinterpret_cast<uint32_t*>(im + il.counters);
     a.point_list = bn ? reinterpret_cast<uint32_t*>(bn + bl.point_list) : nullptr;
     a.keys = bn ? reinterpret_cast<unsigned long long*>(bn + bl.keys) : nullptr;
@@ -324,6 +325,7 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     a.final_T = reinterpret_cast<const float*>(im + il.final_T);
     a.n_contrib = reinterpret_cast<const uint32_t*>(im + il.n_contrib);
     a.last_entry = reinterpret_cast<const uint32_t*>(im + il.last_entry);
+    a.tile_order = reinterpret_cast<const uint32_t*>(im + il.tile_order);
     a.ranges = reinterpret_cast<const uint2*>(im + il.ranges);
     a.point_list = bn ? reinterpret_cast<const uint32_t*>(bn + bl.point_list) : nullptr;
     a.sub_hits = bn ? reinterpret_cast<const uint32_t*>(bn + bl.sub_hits) : nullptr;
@@ -336,7 +338,9 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     if (!ws->acc_zeroed_by_forward &&
         (rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
     // the zero rows of the dense-gradient contract are written on a side stream while the blend backward runs
-    SideStream* side = (!grads->sparse_rows && !debug && !(prm->debug & 32) && prm->P >= 4096) ? side_stream() : nullptr;
+    // (opt-in, debug bit 5: measured SLOWER on C3 / C5 -- 0.42 + 0.135 vs 0.344 + 0.163 ms -- the fill kernel's CTAs take
+    // issue slots from the blend backward, which is issue-bound; kept for frames whose blend backward is short)
+    SideStream* side = (!grads->sparse_rows && !debug && (prm->debug & 32) && prm->P >= 4096) ? side_stream() : nullptr;
     std::unique_lock<std::mutex> side_use;
     if (side) {
         side_use = std::unique_lock<std::mutex>(side->use);

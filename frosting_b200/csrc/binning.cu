@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ list_tiny, uint32_t* __restrict__ list_small,
                  uint32_t* __restrict__ list_large, uint32_t* __restrict__ list_huge,
-                 uint32_t* __restrict__ counters, long long capacity, int32_t* __restrict__ status) {
+                 uint32_t* __restrict__ counters, long long capacity, int32_t* __restrict__ status,
+                 uint32_t* __restrict__ order) {
     __shared__ uint32_t staged[kScanStage];
+    __shared__ uint32_t s_bucket[40];
     __shared__ uint32_t warp_sums[32];
     __shared__ u64 cls_sums[2][32];
     __shared__ u64 cls_total[2];
@@ -126,6 +128,22 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
         run += c;
     }
     atomicMax(&s_max, lmax);
+    // ---- launch order of the blend kernels: longest lists first ----
+    // A tile's blend time grows with its list length and tiles differ by 10-100x; CTAs are dispatched in blockIdx order,
+    // so raster order leaves the SMs that drew a long tile late running alone at the end.  order[] lists the tiles by
+    // descending size class (power-of-two buckets of the instance count; empty tiles last): the classic longest-
+    // processing-time-first heuristic, at the cost of one warp-aggregated counting pass here.
+    if (tid < 40) s_bucket[tid] = 0;
+    __syncthreads();
+    auto bucket_of = [](uint32_t c) { return c ? 31 - (32 - __clz(c)) : 32; };       // big lists -> small bucket index
+    for (int t0 = begin; t0 < end; ++t0) atomicAdd(&s_bucket[bucket_of(cnt[t0])], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run_b = 0;
+        for (int b = 0; b <= 32; ++b) { const uint32_t c = s_bucket[b]; s_bucket[b] = run_b; run_b += c; }
+    }
+    __syncthreads();
+    for (int t0 = begin; t0 < end; ++t0) order[atomicAdd(&s_bucket[bucket_of(cnt[t0])], 1u)] = (uint32_t)t0;
     __syncthreads();
     if (tid == 1023) {
         // the instance count is reported as a non-negative int32: anything beyond that is an overflow whatever the capacity
@@ -635,7 +653,7 @@ tile_sort_global_kernel(const uint32_t* __restrict__ list, const uint32_t* __res
 cudaError_t launch_tile_scan(const FwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
     tile_scan_kernel<<<1, 1024, 0, s>>>(T, a.tile_count, a.ranges, a.cursor, a.list_tiny, a.list_small, a.list_large,
-                                        a.list_huge, a.counters, a.capacity, a.status);
+                                        a.list_huge, a.counters, a.capacity, a.status, a.tile_order);
     count_launch();
     return cudaGetLastError();
 }

@@ -49,14 +49,15 @@ render_bwd_pair_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
-                       float* __restrict__ acc, const int32_t* __restrict__ status, const ExtraArgs ex) {
+                       float* __restrict__ acc, const int32_t* __restrict__ status, const ExtraArgs ex,
+                       const uint32_t* __restrict__ tile_order) {
     __shared__ PairSlab slabs[kWarps];
     __shared__ PairSlabX slabs_x[kExtra ? kWarps : 1];
     if (status[FB200_ST_OVERFLOW]) return;
 
     const unsigned full = 0xffffffffu;
     constexpr int kSplit = kWarpsPerTile / kWarps;
-    const int tile = blockIdx.x / kSplit;
+    const int tile = (int)tile_order[blockIdx.x / kSplit];       // longest lists first (binning.cu)
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const int wslot = threadIdx.x >> 5;
     const int warp = (blockIdx.x % kSplit) * kWarps + wslot;      // sub-tile index inside the tile
@@ -373,13 +374,14 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       const SplatRec* __restrict__ rec, int W, int H, int tiles_x,
                       const float* __restrict__ bg, const float* __restrict__ final_T,
                       const uint32_t* __restrict__ last_entry, const float* __restrict__ dL_dpix,
-                      float* __restrict__ acc, const int32_t* __restrict__ status) {
+                      float* __restrict__ acc, const int32_t* __restrict__ status,
+                      const uint32_t* __restrict__ tile_order) {
     __shared__ BwdWarpSmem smem[kWarps];
     if (status[FB200_ST_OVERFLOW]) return;
 
     const unsigned full = 0xffffffffu;
     constexpr int kSplit = kWarpsPerTile / kWarps;
-    const int tile = blockIdx.x / kSplit;
+    const int tile = (int)tile_order[blockIdx.x / kSplit];       // longest lists first (binning.cu)
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const int wslot = threadIdx.x >> 5;
     const int warp = (blockIdx.x % kSplit) * kWarps + wslot;      // sub-tile index inside the tile
@@ -437,22 +439,26 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const float* const pdp2 = sm.dp2 + 16 * h;
     const uint32_t* const plast = sm.last + 16 * h;
 
-    // The next block's records are fetched into registers while the current block is processed (one dependent hop:
-    // id -> record).  A/B (profiles/r02_tma_ab.md): staging them with one 48-byte cp.async.bulk per record into a 4-deep
-    // shared-memory ring, 3 blocks ahead, was SLOWER (C3: 0.408 vs 0.337 ms) -- 16 small bulk copies per block per warp
-    // exceed what the SM's TMA unit issues, and the warps spin on the mbarriers.
-    uint32_t nid = 0;
+    // Register prefetch, two stages deep: the Gaussian ids of block k+2 and the records of block k+1 are requested while
+    // block k is processed, so neither hop of the dependent chain id -> record is waited for (round-2 v6 profile at C2:
+    // 27 % of the stall samples sat on the id load at the top of every block).  A/B (profiles/r02_tma_ab.md): staging
+    // the records with one 48-byte cp.async.bulk each into a 4-deep shared-memory ring, 3 blocks ahead, was SLOWER
+    // (C3: 0.408 vs 0.337 ms) -- 16 small bulk copies per block per warp exceed what the SM's TMA unit issues and the
+    // warps spin on the mbarriers.
+    auto load_id = [&](int t) -> uint32_t {       // entry t-1-g of the list, 0 if beyond its start
+        const int e = t - 1 - g;
+        return e >= 0 ? __ldg(sub + e) : 0u;
+    };
+    uint32_t nid = load_id(top), nnid = load_id(top - kBlk);
     float4 n0, n1, n2;
     n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](int t) {       // entries t-1 ... t-16 (lane g takes entry t-1-g)
-        const int e = t - 1 - g;
-        if (e >= 0) {
-            nid = sub[e];
-            const float4* p = reinterpret_cast<const float4*>(rec + nid);
+    auto fetch_rec = [&](uint32_t id, int t) {    // records of the block whose top is t
+        if (t - 1 - g >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(rec + id);
             n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2);
         }
     };
-    fetch(top);
+    fetch_rec(nid, top);
 
     while (top > 0) {
         const int cnt = min(kBlk, top);
@@ -463,7 +469,9 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const float cr = valid ? n1.z : 0.f, cg = valid ? n1.w : 0.f, cb = valid ? n2.x : 0.f;
         const uint32_t gid = nid;
         top -= cnt;
-        fetch(top);
+        nid = nnid;
+        fetch_rec(nid, top);                  // next block's records (its ids arrived a block ago)
+        nnid = load_id(top - kBlk);           // ids of the block after that
         // ---- phase 1: alpha of (Gaussian g) x (up to 16 pixels), the forward's op order ----
         // slots that can hold a contributing pixel for some entry of this block (entries [top, top + cnt) after the update)
         const unsigned slots = __ballot_sync(full, pair_last > (uint32_t)top) & 0xffu;
@@ -623,19 +631,19 @@ cudaError_t launch_render_bwd(const BwdArgs& a, cudaStream_t s) {
     if (a.ex.ch > 0)
         render_bwd_pair_kernel<true, kWarps><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
-            a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+            a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex, a.tile_order);
     else if (a.prm.debug & 4)       // A/B switch: the round-1 pair kernel (lane = pixel + butterfly)
         render_bwd_pair_kernel<false, kWarps><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.point_list, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
-            a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex);
+            a.final_T, a.n_contrib, a.dL_dpix, a.acc, a.status, a.ex, a.tile_order);
     else if (a.prm.debug & 16)      // A/B switch: 24 resident warps (80 registers, 13 spilled words) -- measured slower
         render_bwd_t16_kernel<kWarps, 24><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.sub_hits, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
-            a.final_T, a.last_entry, a.dL_dpix, a.acc, a.status);
+            a.final_T, a.last_entry, a.dL_dpix, a.acc, a.status, a.tile_order);
     else                            // 20 resident warps per SM, 96 registers, no spills (C3: 0.336 ms vs 0.362)
         render_bwd_t16_kernel<kWarps, 20><<<grid, 32 * kWarps, 0, s>>>(
             a.ranges, a.sub_hits, a.rec, a.prm.image_width, a.prm.image_height, a.tiles_x, a.in.d_background,
-            a.final_T, a.last_entry, a.dL_dpix, a.acc, a.status);
+            a.final_T, a.last_entry, a.dL_dpix, a.acc, a.status, a.tile_order);
     return cudaGetLastError();
 }
 
