@@ -216,35 +216,6 @@ scatter_kernel(int P, int tiles_x, const uint2* __restrict__ rect, const float* 
     }
 }
 
-// Same job with CTA-private tables (the default): a CTA owns a contiguous slice of the Gaussians, counts its instances
-// per tile in shared memory, reserves ONE contiguous range per touched tile in the tile's segment (one returning global
-// atomic per (CTA, tile) instead of one per instance: C5 36 M -> ~2 M) and then places its instances with shared-memory
-// ranks.  The order inside a tile segment is arbitrary either way; the sort fixes it.
-__global__ void __launch_bounds__(512)
-scatter_chunked_kernel(int P, int T, int tiles_x, const uint2* __restrict__ rect, const float* __restrict__ depth,
-                       uint32_t* __restrict__ cursor, u64* __restrict__ keys, const int32_t* __restrict__ status) {
-    extern __shared__ uint32_t s_tab[];
-    uint32_t* s_cnt = s_tab;            // per tile: this CTA's instances (then: running rank)
-    uint32_t* s_base = s_tab + T;       // per tile: start of this CTA's range in the tile's segment
-    if (status[FB200_ST_OVERFLOW]) return;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) s_cnt[t] = 0;
-    __syncthreads();
-    const int per = ((P + gridDim.x - 1) / gridDim.x + 31) & ~31;
-    const int lo = min(P, (int)blockIdx.x * per), hi = min(P, lo + per);
-    walk_rects(rect, lo, hi, tiles_x, nullptr, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(s_cnt + tile, 1u); });
-    __syncthreads();
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        const uint32_t c = s_cnt[t];
-        s_base[t] = c ? atomicAdd(cursor + t, c) : 0u;
-        s_cnt[t] = 0;
-    }
-    __syncthreads();
-    walk_rects(rect, lo, hi, tiles_x, reinterpret_cast<const uint32_t*>(depth),
-               [&](uint32_t tile, uint32_t gidx, uint32_t dbits) {
-                   keys[s_base[tile] + atomicAdd(s_cnt + tile, 1u)] = ((u64)dbits << 32) | gidx;
-               });
-}
-
 // ---- per-tile sort ----------------------------------------------------------------------------------
 // Stable LSD radix sort of one tile's keys on the 32 depth bits (4 passes of 8 bits; a pass whose digit
 // is the same for every key is skipped), followed by a fix-up that orders runs of EQUAL depth by
@@ -695,20 +666,10 @@ cudaError_t launch_binning(const FwdArgs& a, cudaStream_t s, const int32_t* h_st
         count_launch();
     }
     if (a.prm.P > 0) {
-        const int smem = T * 8;
-        if (smem <= kMaxTileSmem) {
-            if (smem > 48 * 1024) {
-                const cudaError_t attr = cudaFuncSetAttribute(scatter_chunked_kernel,
-                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (attr != cudaSuccess) return attr;
-            }
-            const int grid = max(1, min(148 * 2, (a.prm.P + 4095) / 4096));
-            scatter_chunked_kernel<<<grid, 512, smem, s>>>(a.prm.P, T, a.tiles_x, a.rect, a.depth, a.cursor, a.keys,
-                                                           a.status);
-        } else {
-            scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a.prm.P, a.tiles_x, a.rect, a.depth, a.cursor,
-                                                                 a.keys, a.status);
-        }
+        // (A/B, profiles/r02_binning.md: CTA-private counting / scattering through shared-memory tables was SLOWER at C5
+        // -- 1.21 ms vs 0.52 ms -- shared-memory atomics retire ~2 cycles per lane; the direct global atomics stay)
+        scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, s>>>(a.prm.P, a.tiles_x, a.rect, a.depth, a.cursor,
+                                                             a.keys, a.status);
         count_launch();
     }
     // The work lists live on the device: launch enough CTAs for the worst case, each CTA strides over its list.

@@ -202,7 +202,7 @@ struct CamConst {
     float campos[3];
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 preprocess_fwd_kernel(FwdArgs a) {
     __shared__ CamConst cam;
     if (threadIdx.x < 16) {
@@ -365,35 +365,58 @@ preprocess_fwd_kernel(FwdArgs a) {
         a.rect[idx] = rect;
     }
 
-    // Gaussians with radii > 0 (FB200_ST_NUM_VISIBLE): one atomic per warp that has any
-    const unsigned vis = __ballot_sync(0xffffffffu, radius > 0);
-    if (vis != 0 && (threadIdx.x & 31) == 0) atomicAdd(a.counters + 3, (uint32_t)__popc(vis));
-}
-
-// ---- per-tile instance counts ------------------------------------------------------------------------------------
-// The reference has no such pass (it sorts 64-bit tile|depth keys globally); here the counts size the per-tile segments.
-// Round 1 counted inside preprocess with one global RED per instance: at C5 that is 36 M atomics onto 7 500 addresses
-// (~0.35 ms of a 0.68 ms kernel).  Now each CTA owns a contiguous slice of the Gaussians, counts ITS instances per tile
-// in shared memory (native shared-memory atomics; warp-balanced walk of the tile rectangles, so a 12x12-tile splat does
-// not serialise one lane) and adds its non-zero counts to the global table once: 30-100x fewer global atomics on dense
-// frames, no more on sparse ones.
-template <bool kShared>
-__global__ void __launch_bounds__(512)
-tile_count_kernel(int P, int T, int tiles_x, const uint2* __restrict__ rect, uint32_t* __restrict__ tile_count) {
-    extern __shared__ uint32_t s_hist[];
-    uint32_t* hist = kShared ? s_hist : tile_count;      // frames with more tiles than shared memory holds count globally
-    if (kShared) {
-        for (int t = threadIdx.x; t < T; t += blockDim.x) s_hist[t] = 0;
-        __syncthreads();
+    // ---- per-tile instance counts, warp-balanced ----
+    // The reference's duplicateWithKeys walks each splat's tile rectangle in a serial per-thread double loop
+    // (rasterizer_impl.cu:98-108) and so did round 1's counting here: one 12x12-tile splat kept its warp busy for 144
+    // dependent iterations (C5: preprocess 0.77 ms).  Same expansion as scatter_kernel (binning.cu): the warp scans its
+    // 32 rectangle sizes and walks the concatenated instance list 32 instances per step.
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t minx = rect.x & 0xffffu, miny = rect.x >> 16;
+    const uint32_t w = (rect.y & 0xffffu) - minx;
+    const uint32_t cnt = w * ((rect.y >> 16) - miny);          // 0 unless the Gaussian is rendered
+    const unsigned vis = __ballot_sync(full, cnt != 0);
+    if (vis == 0) return;
+    if (lane == 0) atomicAdd(a.counters + 3, (uint32_t)__popc(vis));      // FB200_ST_NUM_VISIBLE
+    const uint32_t gxw = (uint32_t)a.tiles_x;
+    if (__reduce_max_sync(full, cnt) <= 24u) {
+        // small rectangles everywhere in the warp (the common frame): the plain per-lane walk is cheaper than the scan
+        const uint32_t maxy = rect.y >> 16, maxx = rect.y & 0xffffu;
+        if (cnt != 0)
+            for (uint32_t ty = miny; ty < maxy; ++ty)
+                for (uint32_t tx = minx; tx < maxx; ++tx) atomicAdd(a.tile_count + ty * gxw + tx, 1u);
+        return;
     }
-    const int per = ((P + gridDim.x - 1) / gridDim.x + 31) & ~31;
-    const int lo = min(P, (int)blockIdx.x * per), hi = min(P, lo + per);
-    walk_rects(rect, lo, hi, tiles_x, nullptr, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(hist + tile, 1u); });
-    if (kShared) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < T; t += blockDim.x) {
-            const uint32_t c = s_hist[t];
-            if (c) atomicAdd(tile_count + t, c);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = __shfl_sync(full, incl, 31);
+    const float rw = w ? __frcp_rn((float)w) : 0.f;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t item = base + lane;
+        int pos = 0;                      // owner = number of lanes whose inclusive count is <= item
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t t = __shfl_sync(full, incl, pos + step - 1);
+            if (t <= item) pos += step;
+        }
+        const int owner = min(pos, 31);
+        const uint32_t o_excl = __shfl_sync(full, excl, owner);
+        const uint32_t o_min = __shfl_sync(full, rect.x, owner);
+        const uint32_t o_w = __shfl_sync(full, w, owner);
+        const float o_rw = __shfl_sync(full, rw, owner);
+        if (item < total) {
+            const uint32_t k = item - o_excl;
+            // k / o_w through the reciprocal (both < 2^24), corrected by at most one either way
+            uint32_t q = __float2uint_rz(__fmul_rn((float)k, o_rw));
+            int rem = (int)k - (int)(q * o_w);
+            if (rem < 0) { --q; rem += (int)o_w; } else if (rem >= (int)o_w) { ++q; rem -= (int)o_w; }
+            const uint32_t ty = (o_min >> 16) + q, tx = (o_min & 0xffffu) + (uint32_t)rem;
+            atomicAdd(a.tile_count + ty * gxw + tx, 1u);
         }
     }
 }
@@ -414,24 +437,13 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a, cudaStream_t s) {
     const int T = a.tiles_x * a.tiles_y;
     // the per-tile counts and the counter words behind them (adjacent in the image workspace) in one memset
     const size_t span = (size_t)(reinterpret_cast<const char*>(a.counters) - reinterpret_cast<const char*>(a.tile_count)) + 64;
+    (void)T;
     cudaError_t e = cudaMemsetAsync(a.tile_count, 0, span, s);
     if (e != cudaSuccess) return e;
     if (a.prm.P > 0) {
         const int blocks = (a.prm.P + 255) / 256;
         preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(a);
-        // per-tile instance counts: CTA-private histograms in shared memory (one word per tile)
-        const int smem = T * 4;
-        const int grid = max(1, min(148 * 2, (a.prm.P + 4095) / 4096));
-        if (smem <= kMaxTileSmem) {
-            if (smem > 48 * 1024) {
-                e = cudaFuncSetAttribute(tile_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (e != cudaSuccess) return e;
-            }
-            tile_count_kernel<true><<<grid, 512, smem, s>>>(a.prm.P, T, a.tiles_x, a.rect, a.tile_count);
-        } else {
-            tile_count_kernel<false><<<grid, 512, 0, s>>>(a.prm.P, T, a.tiles_x, a.rect, a.tile_count);
-        }
-        count_launch(2);
+        count_launch();
     }
     return cudaGetLastError();
 }
