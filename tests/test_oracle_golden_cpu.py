@@ -12,7 +12,7 @@ import torch
 from oracle import cpu
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-              if not os.path.basename(p).startswith(("loss_", "adam")))
+              if not os.path.basename(p).startswith(("loss_", "adam", "frosting_")))
 
 
 def _settings(z):
@@ -121,3 +121,53 @@ def test_oracle_binning_is_stable_and_ranges_partition():
             covered[a:b] = True
     assert covered.all()
     assert np.array_equal(cpu.mark_visible(rs, A["means3D"]), A["means3D"][:, 2] > 0.2)
+
+
+def _frosting_golden():
+    import os
+    import numpy as np
+    import torch
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frosting_attrs.npz"))
+    params = {k[len("param_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param_")}
+    mesh = {k[len("mesh_"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("mesh_")}
+    return z, params, mesh
+
+
+def test_frosting_attribute_restatement_is_pinned_to_the_reference_properties():
+    """`scenes.frosting_attributes` -- the oracle of the fused attribute kernels and of bench.py's reference arm -- against
+    vectors produced by EXECUTING the reference's own property source (frosting_model.py:643-799, cut out with ast by
+    tests/golden/make_frosting_attr_golden.py): outputs and autograd gradients."""
+    import numpy as np
+    import torch
+    from frosting_b200 import scenes
+    z, params, mesh = _frosting_golden()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    m = dict(mesh)
+    m["inner"] = mesh["inner"].clone().requires_grad_(True)
+    m["outer"] = mesh["outer"].clone().requires_grad_(True)
+    out = scenes.frosting_attributes(leaf, m)
+    for k, v in out.items():
+        np.testing.assert_allclose(v.detach().numpy(), z[f"out_{k}"], rtol=1e-6, atol=1e-7, err_msg=k)
+    sum((out[k] * torch.from_numpy(z[f"cot_{k}"])).sum() for k in out).backward()
+    for k, v in leaf.items():
+        ref = z[f"grad_{k}"]
+        np.testing.assert_allclose(v.grad.numpy(), ref, rtol=2e-5, atol=2e-6 * np.abs(ref).max(), err_msg=k)
+    # inner = base - t n, outer = base + t n  =>  d/d(base) = d/d(inner) + d/d(outer)
+    both = (m["inner"].grad + m["outer"].grad).numpy()
+    np.testing.assert_allclose(both, z["grad_base_verts"], rtol=2e-5, atol=2e-6 * np.abs(z["grad_base_verts"]).max())
+
+
+def test_frosting_golden_is_reproducible_from_the_reference_tree():
+    """Where /root/reference exists, re-execute the reference's property source and compare with the committed file."""
+    import os
+    import runpy
+    import numpy as np
+    import pytest
+    if not os.path.exists("/root/reference/frosting_scene/frosting_model.py"):
+        pytest.skip("/root/reference not present")
+    here = os.path.dirname(os.path.abspath(__file__))
+    mod = runpy.run_path(os.path.join(here, "golden", "make_frosting_attr_golden.py"), run_name="golden_check")
+    props = mod["reference_properties"]()
+    assert all(hasattr(props, n) for n in mod["WANT"])
+    z, params, mesh = _frosting_golden()
+    assert z["out_means3D"].shape[1] == 3 and np.isfinite(z["out_shs"]).all()

@@ -216,3 +216,25 @@ def test_frosting_render_equals_the_two_step_path(cuda_device):
     dead = radii1 <= 0
     for k in p1:
         assert float(p1[k].grad[dead].abs().sum()) == 0.0, k
+
+
+def test_fused_attribute_kernels_against_reference_property_goldens(cuda_device):
+    """The fused attribute kernels against vectors produced by executing the reference's own property source
+    (tests/golden/make_frosting_attr_golden.py): values 1e-6, gradients 2e-5 of scale, shell-vertex gradients included."""
+    import os
+    import numpy as np
+    dev = cuda_device
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frosting_attrs.npz"))
+    params = {k[len("param_"):]: torch.from_numpy(z[k]).to(dev).requires_grad_(True) for k in z.files if k.startswith("param_")}
+    mesh = {k[len("mesh_"):]: torch.from_numpy(z[k]).to(dev) for k in z.files if k.startswith("mesh_")}
+    mesh["inner"].requires_grad_(True); mesh["outer"].requires_grad_(True)
+    out = fb.frosting_attributes_fused(params, mesh)
+    for k, v in out.items():
+        ref = torch.from_numpy(z[f"out_{k}"]).to(dev)
+        assert (v - ref).abs().max().item() <= 1e-6 * max(1.0, ref.abs().max().item()), k
+    sum((out[k] * torch.from_numpy(z[f"cot_{k}"]).to(dev)).sum() for k in out).backward()
+    for k, v in params.items():
+        ref = torch.from_numpy(z[f"grad_{k}"]).to(dev)
+        assert (v.grad - ref).abs().max().item() <= 2e-5 * ref.abs().max().item(), k
+    ref = torch.from_numpy(z["grad_base_verts"]).to(dev)
+    assert ((mesh["inner"].grad + mesh["outer"].grad) - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
