@@ -350,7 +350,7 @@ def rooflines(prof, R_avg, W, H, workload):
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(key), "kernel": key,
                 "kernel_ms": ms, "algorithmic_bytes": bytes_, "peak_source": peaks["src"],
                 "instances_R": R_avg}
-    return (roof(b_bwd, prof["render_bwd"], traffic.get("bwd_kernel_name", "render_bwd_pair_kernel")),
+    return (roof(b_bwd, prof["render_bwd"], traffic.get("bwd_kernel_name", "render_bwd_t16_kernel")),
             roof(b_fwd, prof["render_fwd"], traffic.get("fwd_kernel_name", "render_fwd_pair_kernel")))
 
 
