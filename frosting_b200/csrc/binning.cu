@@ -136,14 +136,31 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     if (tid < 40) s_bucket[tid] = 0;
     __syncthreads();
     auto bucket_of = [](uint32_t c) { return c ? 31 - (32 - __clz(c)) : 32; };       // big lists -> small bucket index
-    for (int t0 = begin; t0 < end; ++t0) atomicAdd(&s_bucket[bucket_of(cnt[t0])], 1u);
+    // one tile per lane; lanes of a warp that share a bucket are counted / placed with ONE shared-memory atomic
+    // (8 k atomics on ~6 addresses serialise to tens of microseconds otherwise)
+    const unsigned lanemask_lt = (1u << (tid & 31)) - 1u;
+    for (int t0 = tid; t0 < ((T + 31) & ~31); t0 += 1024) {
+        const bool have = t0 < T;
+        const int b = have ? bucket_of(cnt[t0]) : 33;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (have && (peers & lanemask_lt) == 0) atomicAdd(&s_bucket[b], (uint32_t)__popc(peers));
+    }
     __syncthreads();
     if (tid == 0) {
         uint32_t run_b = 0;
         for (int b = 0; b <= 32; ++b) { const uint32_t c = s_bucket[b]; s_bucket[b] = run_b; run_b += c; }
     }
     __syncthreads();
-    for (int t0 = begin; t0 < end; ++t0) order[atomicAdd(&s_bucket[bucket_of(cnt[t0])], 1u)] = (uint32_t)t0;
+    for (int t0 = tid; t0 < ((T + 31) & ~31); t0 += 1024) {
+        const bool have = t0 < T;
+        const int b = have ? bucket_of(cnt[t0]) : 33;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        uint32_t base_b = 0;
+        const int leader = __ffs(peers) - 1;
+        if (have && (peers & lanemask_lt) == 0) base_b = atomicAdd(&s_bucket[b], (uint32_t)__popc(peers));
+        base_b = __shfl_sync(0xffffffffu, base_b, leader);
+        if (have) order[base_b + __popc(peers & lanemask_lt)] = (uint32_t)t0;
+    }
     __syncthreads();
     if (tid == 1023) {
         // the instance count is reported as a non-negative int32: anything beyond that is an overflow whatever the capacity
