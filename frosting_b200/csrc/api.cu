@@ -212,7 +212,6 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     a.depth = reinterpret_cast<float*>(g + gl.depth);
     a.rect = reinterpret_cast<uint2*>(g + gl.rect);
     a.clamped = reinterpret_cast<uint8_t*>(g + gl.clamped);
-    a.survivors = reinterpret_cast<uint32_t*>(g + gl.survivors);
     a.final_T = reinterpret_cast<float*>(im + il.final_T);
     a.n_contrib = reinterpret_cast<uint32_t*>(im + il.n_contrib);
     a.last_entry = reinterpret_cast<uint32_t*>(im + il.last_entry);
@@ -338,17 +337,23 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
 
     if (!ws->acc_zeroed_by_forward &&
         (rc = stage(launch_render_bwd_clear(a, s), "render backward (clear)", debug, s)) != FB200_OK) return rc;
+    // the zero rows of the dense-gradient contract are written on a side stream while the blend backward runs
+    // (opt-in, debug bit 5: measured SLOWER on C3 / C5 -- 0.42 + 0.135 vs 0.344 + 0.163 ms -- the fill kernel's CTAs take
+    // issue slots from the blend backward, which is issue-bound; kept for frames whose blend backward is short)
+    SideStream* side = (!grads->sparse_rows && !debug && (prm->debug & 32) && prm->P >= 4096) ? side_stream() : nullptr;
+    std::unique_lock<std::mutex> side_use;
+    if (side) {
+        side_use = std::unique_lock<std::mutex>(side->use);
+        if ((rc = check(cudaEventRecord(side->fork, s), "fork")) != FB200_OK) return rc;
+        if ((rc = check(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork")) != FB200_OK) return rc;
+        if ((rc = check(launch_zero_rows(a, side->stream), "zero rows")) != FB200_OK) return rc;
+        if ((rc = check(cudaEventRecord(side->join, side->stream), "join")) != FB200_OK) return rc;
+        a.zeroed_elsewhere = 1;
+    }
     { StageTimer t(FB200_STAGE_RENDER_BWD, s);
       if ((rc = stage(launch_render_bwd(a, s), "render backward", debug, s)) != FB200_OK) return rc; }
+    if (side && (rc = check(cudaStreamWaitEvent(s, side->join, 0), "join")) != FB200_OK) return rc;
     { StageTimer t(FB200_STAGE_GEOM_BWD, s);
-      // The dense-gradient contract (zeros for every Gaussian that was not rendered: 300 B each, 540 MB at C3) is written by
-      // a light streaming kernel at full store bandwidth; geom_bwd_kernel (120 registers, 16 warps per SM) then only
-      // touches warps that have something to compute.  (Running the fill on a side stream UNDER the blend backward was
-      // measured slower: it takes issue slots from an issue-bound kernel -- profiles/README.md.)
-      if (!grads->sparse_rows && prm->P >= 4096) {
-          if ((rc = stage(launch_zero_rows(a, s), "zero rows", debug, s)) != FB200_OK) return rc;
-          a.zeroed_elsewhere = 1;
-      }
       if ((rc = stage(launch_geom_bwd(a, s), "geometry backward", debug, s)) != FB200_OK) return rc; }
     if ((rc = stage(launch_extra_grad(a, s), "extra feature gradients", debug, s)) != FB200_OK) return rc;
     return FB200_OK;

@@ -202,51 +202,8 @@ struct CamConst {
     float campos[3];
 };
 
-// Occlusion-culled frames (C3: 90 % of the Gaussians are dropped by the visible-face lookup) run in two kernels: this light
-// one (full occupancy) applies the mask / lookup and the near-plane test, writes the zero radii / rects of the dropped
-// Gaussians and compacts the survivors' indices; the heavy kernel below then runs on full warps of survivors only
-// (template kFromList) instead of on warps where 3 lanes of 32 have work.
-__global__ void __launch_bounds__(256)
-cull_kernel(FwdArgs a, uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors) {
-    __shared__ float vrow[4];
-    if (threadIdx.x < 4) vrow[threadIdx.x] = a.in.d_viewmatrix[4 * threadIdx.x + 2];
-    __syncthreads();
-    const int P = a.prm.P;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
-    if (idx < P) {
-        const bool by_face = a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points;
-        const long long cell = by_face ? __ldg(a.in.d_point_cells + idx) : 0;
-        const uint8_t vis_in = a.in.d_visibility != nullptr ? __ldg(a.in.d_visibility + idx) : (uint8_t)1;
-        const float px = __ldg(a.in.d_means3D + 3 * (size_t)idx + 0);
-        const float py = __ldg(a.in.d_means3D + 3 * (size_t)idx + 1);
-        const float pz = __ldg(a.in.d_means3D + 3 * (size_t)idx + 2);
-        const uint8_t face_in = by_face ? __ldg(a.in.d_face_visible + cell) : (uint8_t)1;
-        // affine_row(view, 2, p): the same ops as the heavy kernel (it recomputes the depth for its sort key)
-        const float depth = fadd(dot3x(px, vrow[0], py, vrow[1], pz, vrow[2]), vrow[3]);
-        keep = !(depth <= 0.2f);
-        if (!keep && a.prm.prefiltered) {
-            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-            __trap();
-        }
-        if (vis_in == 0 || face_in == 0) keep = false;
-        if (!keep) {
-            a.radii[idx] = 0;
-            a.rect[idx] = make_uint2(0u, 0u);
-        }
-    }
-    const unsigned bits = __ballot_sync(0xffffffffu, keep);
-    if (bits == 0) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(n_survivors, (uint32_t)__popc(bits));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) survivors[base + __popc(bits & ((1u << lane) - 1u))] = (uint32_t)idx;
-}
-
-template <bool kFromList>
 __global__ void __launch_bounds__(256, 4)
-preprocess_fwd_kernel(FwdArgs a, const uint32_t* __restrict__ survivors, const uint32_t* __restrict__ n_survivors) {
+preprocess_fwd_kernel(FwdArgs a) {
     __shared__ CamConst cam;
     if (threadIdx.x < 16) {
         cam.view[threadIdx.x] = a.in.d_viewmatrix[threadIdx.x];
@@ -257,20 +214,17 @@ preprocess_fwd_kernel(FwdArgs a, const uint32_t* __restrict__ survivors, const u
 
     const int P = a.prm.P;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    // no early exit of single lanes: the tile counting at the end is warp-cooperative
-    const int n_items = kFromList ? (int)*n_survivors : P;
-    if (kFromList && (tid & ~31) >= n_items) return;             // whole warp beyond the list
-    const bool valid = tid < n_items;
-    const int idx = kFromList ? (int)survivors[valid ? tid : n_items - 1] : (valid ? tid : P - 1);
+    const bool valid = tid < P;          // no early exit: the tile counting at the end is warp-cooperative
+    const int idx = valid ? tid : P - 1;
 
     const float* __restrict__ v = cam.view;
     const float* __restrict__ m = cam.proj;
 
     // the occlusion inputs first: the cell -> visible-face gather is a dependent chain of its own, started before the
     // position loads so that the two chains overlap (a culled Gaussian then costs two memory round trips, not three)
-    const bool by_face = !kFromList && a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points;
+    const bool by_face = a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points;
     const long long cell = by_face ? __ldg(a.in.d_point_cells + idx) : 0;
-    const uint8_t vis_in = (!kFromList && a.in.d_visibility != nullptr) ? __ldg(a.in.d_visibility + idx) : (uint8_t)1;
+    const uint8_t vis_in = a.in.d_visibility != nullptr ? __ldg(a.in.d_visibility + idx) : (uint8_t)1;
     const float px = __ldg(a.in.d_means3D + 3 * (size_t)idx + 0);
     const float py = __ldg(a.in.d_means3D + 3 * (size_t)idx + 1);
     const float pz = __ldg(a.in.d_means3D + 3 * (size_t)idx + 2);
@@ -488,15 +442,8 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     if (a.prm.P > 0) {
         const int blocks = (a.prm.P + 255) / 256;
-        if (a.in.d_visibility != nullptr || a.in.d_face_visible != nullptr) {
-            cull_kernel<<<blocks, 256, 0, s>>>(a, a.survivors, a.counters + 5);
-            // the list lives on the device: launched for the worst case, warps beyond the list exit at once
-            preprocess_fwd_kernel<true><<<blocks, 256, 0, s>>>(a, a.survivors, a.counters + 5);
-            count_launch(2);
-        } else {
-            preprocess_fwd_kernel<false><<<blocks, 256, 0, s>>>(a, nullptr, nullptr);
-            count_launch();
-        }
+        preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(a);
+        count_launch();
     }
     return cudaGetLastError();
 }

@@ -603,14 +603,12 @@ render_bwd_t16_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         if (h == 0 && ((act16 >> g) & 1u)) {
             float* a = acc + (size_t)gid * 12;
             // dG/ddelx = -G (dx A + dy B), dG/ddely = -G (dy C + dx B)   (backward.cu:536-546)
-            atomicAdd(a + 0, -ddelx_dx * fmaf(A, v[0], B * v[1]));
-            atomicAdd(a + 1, -ddely_dy * fmaf(Cc, v[1], B * v[0]));
-            atomicAdd(a + 2, -0.5f * v[2]);
-            atomicAdd(a + 3, -0.5f * v[3]);
-            atomicAdd(a + 4, -0.5f * v[4]);
-            atomicAdd(a + 5, v[5]);
-            atomicAdd(a + 6, v[6]);
-            atomicAdd(a + 7, v[7]);
+            // two 128-bit vector reductions + one scalar (red.global.add.v4.f32, sm_90+): a third of the L2 atomic
+            // transactions of nine scalar ones -- neighbouring sub-tiles hit the same 48-byte accumulator records
+            atomicAdd(reinterpret_cast<float4*>(a),
+                      make_float4(-ddelx_dx * fmaf(A, v[0], B * v[1]), -ddely_dy * fmaf(Cc, v[1], B * v[0]),
+                                  -0.5f * v[2], -0.5f * v[3]));
+            atomicAdd(reinterpret_cast<float4*>(a) + 1, make_float4(-0.5f * v[4], v[5], v[6], v[7]));
             atomicAdd(a + 8, v[8]);
         }
         __syncwarp();      // the matrices are rewritten by the next block

@@ -48,6 +48,7 @@ EXACT_BINNING = os.environ.get("FB200_EXACT_BINNING", "0") == "1"
 BWD_PAIR_KERNEL = os.environ.get("FB200_BWD_PAIR", "0") == "1"
 # FB200_FWD_TMA=1: A/B switch, forward blend staged by 1-D cp.async.bulk copies of a packed record stream (debug bit 3)
 FWD_TMA = os.environ.get("FB200_FWD_TMA", "0") == "1"
+ZERO_OVERLAP = os.environ.get("FB200_ZERO_OVERLAP", "0") == "1"   # A/B: dense zero rows on a side stream under the blend bwd (bit 5)
 BWD_OCC24 = os.environ.get("FB200_BWD_OCC24", "0") == "1"      # A/B: backward blend at 24 resident warps / SM (debug bit 4)
 _HEADROOM = 2.0           # speculative capacity = _HEADROOM x (largest count seen for this problem size) + 64 Ki
 _RING = 8                 # status mailboxes in flight per (thread, device)
@@ -243,7 +244,7 @@ def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     prm = Params(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=int(M), image_width=W, image_height=H,
                  tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
                  scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
-                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0) | (4 if BWD_PAIR_KERNEL else 0) | (8 if FWD_TMA else 0) | (16 if BWD_OCC24 else 0), extra=None)
+                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0) | (4 if BWD_PAIR_KERNEL else 0) | (8 if FWD_TMA else 0) | (16 if BWD_OCC24 else 0) | (32 if ZERO_OVERLAP else 0), extra=None)
     inp = Inputs(d_background=_ptr(bg), d_means3D=_ptr(means3D), d_shs=_ptr(sh),
                  d_colors_precomp=_ptr(colors_precomp), d_opacities=_ptr(opacities), d_scales=_ptr(scales),
                  d_rotations=_ptr(rotations), d_cov3D_precomp=_ptr(cov3Ds_precomp),
