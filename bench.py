@@ -490,6 +490,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="developer runs: headline + stage profile only")
     ap.add_argument("--with-dp", action="store_true", help="with --quick: also run the data-parallel training leg")
+    ap.add_argument("--frame", default="raster", choices=["raster", "frosting"],
+                    help="developer runs: time the frame from Frosting's parameters (frosting_render) as the main loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: route fd 1 to stderr for the whole run (NCCL / C libraries print their
@@ -521,7 +523,7 @@ def main():
             return
 
     wl = load_workload(args.workload, device, rank, world, args.impl, local_rank, RING_RADIUS)
-    step = make_step(args.impl, wl, device)
+    step = make_step(args.impl, wl, device, mode=args.frame) if args.frame != "raster" else make_step(args.impl, wl, device)
     log(f"[bench] rank {rank}: workload {args.workload} built in {wl['gen_s']:.1f}s, impl={args.impl}")
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
