@@ -7,7 +7,7 @@ by hand-written CUDA behind the C ABI of include/frosting_b200.h.  See DESIGN.md
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians,
                          forward_with_state)
 from .frosting_attrs import frosting_attributes_fused
-from .frosting_render import frosting_render
+from .frosting_render import frosting_render, frosting_render_two_step
 from .loss import l1_dssim_loss
 from .optim import FrostingAdam, OptimizationParams
 from .mesh import (MeshRasterizer, RasterizationSettings, Fragments, nvdiff_rasterization,
@@ -17,7 +17,7 @@ __all__ = [
     "GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "forward_with_state",
     "MeshRasterizer", "RasterizationSettings", "Fragments", "nvdiff_rasterization",
     "nvdiff_rasterization_with_pix_to_face", "rasterize_mesh", "gaussian_render_mask",
-    "install_as_diff_gaussian_rasterization", "frosting_attributes_fused", "frosting_render", "l1_dssim_loss", "FrostingAdam", "OptimizationParams",
+    "install_as_diff_gaussian_rasterization", "frosting_attributes_fused", "frosting_render", "frosting_render_two_step", "l1_dssim_loss", "FrostingAdam", "OptimizationParams",
 ]
 
 

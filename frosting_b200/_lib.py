@@ -24,7 +24,7 @@ EXPORTED = [
     "fb200_adam_step", "fb200_peer_alloc", "fb200_peer_free", "fb200_peer_export", "fb200_peer_open", "fb200_peer_close",
 ]
 NUM_STAGES = 5
-ABI_VERSION = 3
+ABI_VERSION = 4
 STAGES = ("preprocess", "binning", "render_fwd", "render_bwd", "geom_bwd")
 
 
@@ -47,7 +47,8 @@ class Inputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_background", "d_means3D", "d_shs", "d_colors_precomp", "d_opacities", "d_scales",
         "d_rotations", "d_cov3D_precomp", "d_viewmatrix", "d_projmatrix", "d_campos", "d_visibility",
-        "d_point_cells", "d_face_visible")] + [("n_cell_points", C.c_int64)]
+        "d_point_cells", "d_face_visible")] + [("n_cell_points", C.c_int64),
+                                               ("frosting", C.c_void_p)]     # const fb200_frosting_params* or NULL
 
 
 class Workspace(C.Structure):
@@ -66,7 +67,8 @@ class Workspace(C.Structure):
 class Grads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dopacity", "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh",
-        "d_dL_dscales", "d_dL_drotations")] + [("sparse_rows", C.c_int32)]
+        "d_dL_dscales", "d_dL_drotations")] + [("sparse_rows", C.c_int32),
+                                               ("frosting", C.c_void_p)]   # const fb200_frosting_grads* or NULL
 
 
 class FrostingParams(C.Structure):
@@ -94,7 +96,9 @@ class AdamArgs(C.Structure):
                 ("group_start", C.c_int64 * (ADAM_MAX_GROUPS + 1)), ("lr", C.c_float * ADAM_MAX_GROUPS),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_float),
                 ("bias_correction1", C.c_float), ("bias_correction2_sqrt", C.c_float), ("grad_scale", C.c_float),
-                ("mc_grads", C.c_void_p), ("mc_params", C.c_void_p)]
+                ("mc_grads", C.c_void_p), ("mc_params", C.c_void_p),
+                ("peer_row_radii", C.c_void_p * MAX_PEERS), ("row_width", C.c_int32 * ADAM_MAX_GROUPS),
+                ("row_count", C.c_int32)]
 
 
 class Layout(C.Structure):

@@ -36,13 +36,57 @@ int stage(cudaError_t e, const char* what, bool debug, cudaStream_t s) {
     return FB200_OK;
 }
 
+int check_frosting(const fb200_frosting_params* fp) {
+    if (!fp) return fail(FB200_EINVAL, "frosting_attributes: null params%s");
+    if (fp->P < 0 || fp->sh_rest < 0 || fp->n_verts < 0 || fp->n_faces < 0)
+        return fail(FB200_EINVAL, "frosting_attributes: bad extents%s");
+    if (fp->P > 0 && (!fp->d_bary_logits || !fp->d_cells || !fp->d_faces || !fp->d_inner_verts || !fp->d_outer_verts ||
+                      !fp->d_opacity_logits || !fp->d_log_scales || !fp->d_quats || !fp->d_sh_dc ||
+                      (fp->sh_rest > 0 && !fp->d_sh_rest)))
+        return fail(FB200_EINVAL, "frosting_attributes: missing parameter pointer%s");
+    if (fp->P > 0 && ((reinterpret_cast<uintptr_t>(fp->d_bary_logits) & 7) || (reinterpret_cast<uintptr_t>(fp->d_quats) & 15)))
+        return fail(FB200_EINVAL, "frosting_attributes: bary logits must be 8-byte, quats 16-byte aligned%s");
+    return FB200_OK;
+}
+
+// frosting mode (fb200_inputs.frosting): the rasterizer's own inputs are derived from the parameter block
+int validate_frosting(const fb200_params* prm, const fb200_inputs* in) {
+    const fb200_frosting_params* fp = in->frosting;
+    int rc = check_frosting(fp);
+    if (rc != FB200_OK) return rc;
+    if (in->d_means3D || in->d_shs || in->d_colors_precomp || in->d_opacities || in->d_scales || in->d_rotations ||
+        in->d_cov3D_precomp || in->d_visibility || in->d_point_cells || in->d_face_visible)
+        return fail(FB200_EINVAL, "frosting mode: the attribute / mask pointers of fb200_inputs must be NULL%s");
+    if (fp->P != prm->P || prm->sh_coeffs != fp->sh_rest + 1 || fp->sh_rest > 15)
+        return fail(FB200_EINVAL, "frosting mode: P / sh_coeffs do not match the parameter block (sh_rest <= 15)%s");
+    if (prm->sh_degree < 0 || prm->sh_degree > 3 || (prm->sh_degree + 1) * (prm->sh_degree + 1) > prm->sh_coeffs)
+        return fail(FB200_EINVAL, "sh_degree / sh_coeffs inconsistent%s");
+    if ((reinterpret_cast<uintptr_t>(fp->d_quats) & 15) || (reinterpret_cast<uintptr_t>(fp->d_bary_logits) & 7))
+        return fail(FB200_EINVAL, "frosting mode: quats must be 16-byte aligned, bary logits 8-byte aligned%s");
+    if (prm->extra) return fail(FB200_EINVAL, "frosting mode: extra feature channels are not supported%s");
+    return FB200_OK;
+}
+
+// the fb200_inputs the kernels see in frosting mode: culling inputs taken from the parameter block
+fb200_inputs frosting_inputs(const fb200_inputs* in) {
+    fb200_inputs r = *in;
+    const fb200_frosting_params* fp = in->frosting;
+    r.d_visibility = fp->d_mask;
+    if (fp->d_face_visible) { r.d_point_cells = fp->d_cells; r.d_face_visible = fp->d_face_visible; r.n_cell_points = fp->P; }
+    r.frosting = nullptr;     // a host pointer: never dereferenced on the device
+    return r;
+}
+
 int validate(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws) {
     if (!prm || !in || !ws) return fail(FB200_EINVAL, "null argument struct%s");
     if (prm->P < 0 || prm->image_width <= 0 || prm->image_height <= 0)
         return fail(FB200_EINVAL, "bad extents (P >= 0, image dims > 0 required)%s");
     if (prm->image_width > 65535 * FB200_TILE || prm->image_height > 65535 * FB200_TILE)
         return fail(FB200_EINVAL, "image too large for 16-bit tile coordinates%s");
-    if (prm->P > 0) {
+    if (in->frosting) {
+        int rc = validate_frosting(prm, in);
+        if (rc != FB200_OK) return rc;
+    } else if (prm->P > 0) {
         if (!in->d_means3D || !in->d_opacities) return fail(FB200_EINVAL, "means3D / opacities missing%s");
         const bool has_sh = in->d_shs != nullptr, has_col = in->d_colors_precomp != nullptr;
         if (has_sh == has_col)
@@ -204,6 +248,7 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     memset(&a, 0, sizeof(a));
     a.prm = *prm;
     a.in = *in;
+    if (in->frosting) { a.frosting = 1; a.fr = *in->frosting; a.in = frosting_inputs(in); }
     // focal lengths exactly as rasterizer_impl.cu:222-223
     a.focal_y = prm->image_height / (2.0f * prm->tanfovy);
     a.focal_x = prm->image_width / (2.0f * prm->tanfovx);
@@ -212,6 +257,7 @@ static int setup_fwd(const fb200_params* prm, const fb200_inputs* in, const fb20
     a.depth = reinterpret_cast<float*>(g + gl.depth);
     a.rect = reinterpret_cast<uint2*>(g + gl.rect);
     a.clamped = reinterpret_cast<uint8_t*>(g + gl.clamped);
+    a.vis_list = reinterpret_cast<uint32_t*>(g + gl.vis_list);
     a.final_T = reinterpret_cast<float*>(im + il.final_T);
     a.n_contrib = reinterpret_cast<uint32_t*>(im + il.n_contrib);
     a.last_entry = reinterpret_cast<uint32_t*>(im + il.last_entry);
@@ -293,7 +339,18 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     if (!grads || !d_dL_dout_color || (prm->P > 0 && !d_radii)) return fail(FB200_EINVAL, "backward pointers missing%s");
     // outputs a caller cannot use may be NULL and are then not written: dL/dcolors on the SH path (an intermediate
     // there), dL/dcov3D on the scale/rotation path, dL/dscales + dL/drotations on the precomputed-covariance path
-    if (prm->P > 0 && (!grads->d_dL_dmeans2D || !grads->d_dL_dopacity || !grads->d_dL_dmeans3D ||
+    const fb200_frosting_grads* fg = grads->frosting;
+    if (in->frosting) {
+        if (!fg) return fail(FB200_EINVAL, "frosting mode: fb200_grads.frosting missing%s");
+        if (prm->P > 0 && (!fg->d_bary_logits || !fg->d_opacity_logits || !fg->d_log_scales || !fg->d_quats || !fg->d_sh_dc ||
+                           (in->frosting->sh_rest > 0 && !fg->d_sh_rest) ||
+                           ((fg->d_inner_verts == nullptr) != (fg->d_outer_verts == nullptr))))
+            return fail(FB200_EINVAL, "frosting mode: parameter-gradient pointers missing%s");
+        if ((reinterpret_cast<uintptr_t>(fg->d_quats) & 15) || (reinterpret_cast<uintptr_t>(fg->d_bary_logits) & 7))
+            return fail(FB200_EINVAL, "frosting mode: dL/dquats must be 16-byte aligned, dL/dbary 8-byte aligned%s");
+    } else if (fg) {
+        return fail(FB200_EINVAL, "fb200_grads.frosting given without fb200_inputs.frosting%s");
+    } else if (prm->P > 0 && (!grads->d_dL_dmeans2D || !grads->d_dL_dopacity || !grads->d_dL_dmeans3D ||
                        (in->d_colors_precomp && !grads->d_dL_dcolors) || (in->d_cov3D_precomp && !grads->d_dL_dcov3D) ||
                        (!in->d_cov3D_precomp && (!grads->d_dL_dscales || !grads->d_dL_drotations)) ||
                        (in->d_shs && prm->sh_coeffs > 0 && !grads->d_dL_dsh)))
@@ -316,11 +373,13 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     memset(&a, 0, sizeof(a));
     a.prm = *prm;
     a.in = *in;
+    if (in->frosting) { a.frosting = 1; a.fr = *in->frosting; a.fg = *fg; a.in = frosting_inputs(in); }
     a.focal_y = prm->image_height / (2.0f * prm->tanfovy);
     a.focal_x = prm->image_width / (2.0f * prm->tanfovx);
     a.tiles_x = il.tiles_x; a.tiles_y = il.tiles_y;
     a.rec = reinterpret_cast<const SplatRec*>(g + gl.rec);
     a.clamped = reinterpret_cast<const uint8_t*>(g + gl.clamped);
+    a.vis_list = reinterpret_cast<const uint32_t*>(g + gl.vis_list);
     a.acc = reinterpret_cast<float*>(g + gl.acc);
     a.final_T = reinterpret_cast<const float*>(im + il.final_T);
     a.n_contrib = reinterpret_cast<const uint32_t*>(im + il.n_contrib);
@@ -340,7 +399,7 @@ int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_
     // the zero rows of the dense-gradient contract are written on a side stream while the blend backward runs
     // (opt-in, debug bit 5: measured SLOWER on C3 / C5 -- 0.42 + 0.135 vs 0.344 + 0.163 ms -- the fill kernel's CTAs take
     // issue slots from the blend backward, which is issue-bound; kept for frames whose blend backward is short)
-    SideStream* side = (!grads->sparse_rows && !debug && (prm->debug & 32) && prm->P >= 4096) ? side_stream() : nullptr;
+    SideStream* side = (!grads->sparse_rows && !in->frosting && !debug && (prm->debug & 32) && prm->P >= 4096) ? side_stream() : nullptr;
     std::unique_lock<std::mutex> side_use;
     if (side) {
         side_use = std::unique_lock<std::mutex>(side->use);
@@ -390,17 +449,6 @@ int fb200_gaussian_mask_from_faces(int32_t n_points, const int64_t* d_point_cell
     return check(launch_mask_from_faces(n_points, reinterpret_cast<const long long*>(d_point_cell_indices), F,
                                         d_face_visible, n_background, d_mask, static_cast<cudaStream_t>(stream)),
                  "gaussian_mask_from_faces");
-}
-
-static int check_frosting(const fb200_frosting_params* fp) {
-    if (!fp) return fail(FB200_EINVAL, "frosting_attributes: null params%s");
-    if (fp->P < 0 || fp->sh_rest < 0 || fp->n_verts < 0 || fp->n_faces < 0)
-        return fail(FB200_EINVAL, "frosting_attributes: bad extents%s");
-    if (fp->P > 0 && (!fp->d_bary_logits || !fp->d_cells || !fp->d_faces || !fp->d_inner_verts || !fp->d_outer_verts ||
-                      !fp->d_opacity_logits || !fp->d_log_scales || !fp->d_quats || !fp->d_sh_dc ||
-                      (fp->sh_rest > 0 && !fp->d_sh_rest)))
-        return fail(FB200_EINVAL, "frosting_attributes: missing parameter pointer%s");
-    return FB200_OK;
 }
 
 int fb200_frosting_attributes(const fb200_frosting_params* fp, float* d_means3D, float* d_opacities, float* d_scales,
@@ -468,6 +516,19 @@ int fb200_adam_step(const fb200_adam_args* a, void* stream) {
     }
     if ((a->mc_grads == nullptr) != (a->mc_params == nullptr))
         return fail(FB200_EINVAL, "adam_step: give both multicast mappings or neither%s");
+    {
+        int given = 0;
+        for (int p = 0; p < a->world; ++p) given += a->peer_row_radii[p] != nullptr;
+        if (given != 0 && given != a->world) return fail(FB200_EINVAL, "adam_step: give every rank's row radii or none%s");
+        if (given) {
+            if (a->row_count < 1) return fail(FB200_EINVAL, "adam_step: row_count must be positive with row radii%s");
+            for (int g = 0; g < a->n_groups; ++g) {
+                const int64_t n = a->group_start[g + 1] - a->group_start[g];
+                if (a->row_width[g] < 0 || (int64_t)a->row_width[g] * a->row_count > n || n > 0xffffffffLL)
+                    return fail(FB200_EINVAL, "adam_step: row_width * row_count exceeds the group%s");
+            }
+        }
+    }
     if (!(a->bias_correction1 > 0.f) || !(a->bias_correction2_sqrt > 0.f))
         return fail(FB200_EINVAL, "adam_step: bias corrections must be positive (step >= 1)%s");
     return check(launch_adam_shard(*a, static_cast<cudaStream_t>(stream)), "adam_step");

@@ -12,6 +12,7 @@
 // skips the Gaussians the rasterizer will drop anyway.  Values are tolerance-level (torch's own softmax /
 // normalize roundings are not part of the reference rasterizer's bit-exact contract): 1e-6 relative.
 #include "common.cuh"
+#include "frosting_attr.cuh"
 
 namespace fb200 {
 
@@ -28,18 +29,6 @@ struct AttrBwdArgs {
     float* g_bary; float* g_inner; float* g_outer; float* g_opacity_logits; float* g_log_scales; float* g_quats;
     float* g_sh_dc; float* g_sh_rest;
 };
-
-__device__ __forceinline__ void softmax6(const float* __restrict__ l, float* w) {
-    float m = l[0];
-#pragma unroll
-    for (int k = 1; k < 6; ++k) m = fmaxf(m, l[k]);
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { w[k] = expf(l[k] - m); s += w[k]; }
-    const float inv = 1.0f / s;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) w[k] *= inv;
-}
 
 constexpr int kAttrThreads = 128;
 constexpr int kMaxRest = 15;                       // SH degree 3: 15 "rest" coefficients -> 45 floats per row
@@ -74,29 +63,16 @@ frosting_attr_fwd_kernel(AttrArgs a) {
     if (!live) return;
     const size_t i = (size_t)idx;
     // position
-    float l[6], w[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
-    softmax6(l, w);
-    const long long cell = a.p.d_cells[i];
-    const int vid[3] = {a.p.d_faces[3 * cell], a.p.d_faces[3 * cell + 1], a.p.d_faces[3 * cell + 2]};
-    float px = 0.f, py = 0.f, pz = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float* vi = a.p.d_inner_verts + 3 * (size_t)vid[k];
-        const float* vo = a.p.d_outer_verts + 3 * (size_t)vid[k];
-        px += w[k] * __ldg(vi) + w[3 + k] * __ldg(vo);
-        py += w[k] * __ldg(vi + 1) + w[3 + k] * __ldg(vo + 1);
-        pz += w[k] * __ldg(vi + 2) + w[3 + k] * __ldg(vo + 2);
-    }
+    float w[6], px, py, pz;
+    int vid[3];
+    frost_point(a.p, i, w, vid, px, py, pz);
     a.means3D[3 * i] = px; a.means3D[3 * i + 1] = py; a.means3D[3 * i + 2] = pz;
     // opacity, scale, rotation
-    a.opacities[i] = 1.0f / (1.0f + expf(-__ldg(a.p.d_opacity_logits + i)));
+    a.opacities[i] = frost_sigmoid(__ldg(a.p.d_opacity_logits + i));
 #pragma unroll
     for (int k = 0; k < 3; ++k) a.scales[3 * i + k] = expf(__ldg(a.p.d_log_scales + 3 * i + k));
-    const float4 q = __ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i);
-    const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);   // F.normalize eps
-    reinterpret_cast<float4*>(a.rotations)[i] = make_float4(q.x / nrm, q.y / nrm, q.z / nrm, q.w / nrm);
+    float nrm;
+    reinterpret_cast<float4*>(a.rotations)[i] = frost_normalize(__ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i), nrm);
     // SH: dc | rest -> [M,3]
     float* sh = a.shs + i * (size_t)(R + 1) * 3;
     const float d0 = __ldg(a.p.d_sh_dc + 3 * i), d1 = __ldg(a.p.d_sh_dc + 3 * i + 1), d2 = __ldg(a.p.d_sh_dc + 3 * i + 2);
@@ -162,44 +138,19 @@ frosting_attr_bwd_kernel(AttrBwdArgs a) {
     float4 g_q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
         // position: d/dw_k = <g, vert_k>, softmax backward, vertices get w_k * g (scatter-add)
-        float l[6], w[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) l[k] = __ldg(a.p.d_bary_logits + 6 * i + k);
-        softmax6(l, w);
-        const float gx = a.g_means3D[3 * i], gy = a.g_means3D[3 * i + 1], gz = a.g_means3D[3 * i + 2];
-        const long long cell = a.p.d_cells[i];
-        const int vid[3] = {a.p.d_faces[3 * cell], a.p.d_faces[3 * cell + 1], a.p.d_faces[3 * cell + 2]};
-        float dw[6];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float* vi = a.p.d_inner_verts + 3 * (size_t)vid[k];
-            const float* vo = a.p.d_outer_verts + 3 * (size_t)vid[k];
-            dw[k] = gx * __ldg(vi) + gy * __ldg(vi + 1) + gz * __ldg(vi + 2);
-            dw[3 + k] = gx * __ldg(vo) + gy * __ldg(vo + 1) + gz * __ldg(vo + 2);
-            if (a.g_inner != nullptr && (gx != 0.f || gy != 0.f || gz != 0.f)) {
-                float* di = a.g_inner + 3 * (size_t)vid[k];
-                float* dout = a.g_outer + 3 * (size_t)vid[k];
-                atomicAdd(di, w[k] * gx); atomicAdd(di + 1, w[k] * gy); atomicAdd(di + 2, w[k] * gz);
-                atomicAdd(dout, w[3 + k] * gx); atomicAdd(dout + 1, w[3 + k] * gy); atomicAdd(dout + 2, w[3 + k] * gz);
-            }
-        }
-        float dot = 0.f;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) dot += w[k] * dw[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) gb[k] = w[k] * (dw[k] - dot);
+        float w[6], px, py, pz;
+        int vid[3];
+        frost_point(a.p, i, w, vid, px, py, pz);
+        frost_point_backward(a.p, w, vid, a.g_means3D[3 * i], a.g_means3D[3 * i + 1], a.g_means3D[3 * i + 2],
+                             a.g_inner, a.g_outer, gb);
         // sigmoid, exp
-        const float sg = 1.0f / (1.0f + expf(-__ldg(a.p.d_opacity_logits + i)));
+        const float sg = frost_sigmoid(__ldg(a.p.d_opacity_logits + i));
         g_op = a.g_opacities[i] * sg * (1.0f - sg);
 #pragma unroll
         for (int k = 0; k < 3; ++k) g_ls[k] = a.g_scales[3 * i + k] * expf(__ldg(a.p.d_log_scales + 3 * i + k));
-        // normalize: d/dq = (g - n <n, g>) / |q|
-        const float4 q = __ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i);
-        const float4 g = reinterpret_cast<const float4*>(a.g_rotations)[i];
-        const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
-        const float nx = q.x / nrm, ny = q.y / nrm, nz = q.z / nrm, nw = q.w / nrm;
-        const float ng = nx * g.x + ny * g.y + nz * g.z + nw * g.w;
-        g_q = make_float4((g.x - nx * ng) / nrm, (g.y - ny * ng) / nrm, (g.z - nz * ng) / nrm, (g.w - nw * ng) / nrm);
+        float nrm;
+        const float4 n = frost_normalize(__ldg(reinterpret_cast<const float4*>(a.p.d_quats) + i), nrm);
+        g_q = frost_normalize_backward(n, nrm, reinterpret_cast<const float4*>(a.g_rotations)[i]);
     }
     // SH split: dc gradient to registers, rest gradient rows to the staging block (or straight to memory)
     const float* gsh = a.g_shs + i * (size_t)(R + 1) * 3;

@@ -17,6 +17,7 @@
 //   * denom2inv = 1 / (det^2 + 1e-7) (backward.cu:203) and its == 0 guard,
 //   * the 1.3*tanfov clamp masks on d/dt.x, d/dt.y (backward.cu:175-176).
 #include "common.cuh"
+#include "frosting_attr.cuh"
 
 namespace fb200 {
 
@@ -42,7 +43,6 @@ __device__ __forceinline__ V3 symv(const float* c, V3 t) {
 }
 
 constexpr int kGeomThreads = 128;
-constexpr int kShRow = 13;   // float4 per staged SH-gradient row: 12 + 1 pad => conflict-free 128-bit accesses
 
 // coalesced zero fill of `n4` float4 starting at a 16-byte aligned address, by one warp
 __device__ __forceinline__ void warp_zero4(float* base, int n4, int lane) {
@@ -64,11 +64,29 @@ __device__ __forceinline__ void zero_warp_rows(const BwdArgs& a, size_t g, int M
         for (int k = lane; k < M * 3 * 32; k += 32) a.g.d_dL_dsh[(size_t)M * 3 * g + k] = 0.f;
 }
 
-// The dense-gradient contract of the reference (zeros for every Gaussian that was not rendered: 300 B each, 540 MB of
-// stores at C3) is pure HBM traffic with no dependence on the blend backward, which is issue-bound and leaves HBM idle
-// (3 % of peak): this kernel writes those zero rows on a side stream WHILE the blend backward runs; geom_bwd_kernel then
-// only handles the warps with something to compute.
-__global__ void __launch_bounds__(128)
+// zero gradient row of ONE Gaussian
+__device__ __forceinline__ void zero_row(const BwdArgs& a, size_t i, int M) {
+    for (int k = 0; k < 3; ++k) {
+        a.g.d_dL_dmeans2D[3 * i + k] = 0.f; a.g.d_dL_dmeans3D[3 * i + k] = 0.f;
+        if (a.g.d_dL_dcolors) a.g.d_dL_dcolors[3 * i + k] = 0.f;
+        if (a.g.d_dL_dscales) a.g.d_dL_dscales[3 * i + k] = 0.f;
+    }
+    a.g.d_dL_dopacity[i] = 0.f;
+    if (a.g.d_dL_dcov3D) for (int k = 0; k < 6; ++k) a.g.d_dL_dcov3D[6 * i + k] = 0.f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.g.d_dL_drotations) reinterpret_cast<float4*>(a.g.d_dL_drotations)[i] = z4;
+    if (a.g.d_dL_dsh != nullptr && M == 16) {
+        float4* p = reinterpret_cast<float4*>(a.g.d_dL_dsh + 48 * i);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) p[k] = z4;
+    } else if (a.g.d_dL_dsh != nullptr) {
+        for (int k = 0; k < 3 * M; ++k) a.g.d_dL_dsh[(size_t)M * 3 * i + k] = 0.f;
+    }
+}
+
+// Opt-in (debug bit 5): the runs of 32 rows nobody rendered -- the bulk of the dense contract's zero rows under occlusion
+// culling -- zero-filled on a side stream while the blend backward runs; geom_bwd_kernel then skips them.
+__global__ void __launch_bounds__(256)
 zero_rows_kernel(BwdArgs a) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -80,10 +98,118 @@ zero_rows_kernel(BwdArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(kGeomThreads)
+// ---- one row per lane <-> shared staging block, moved by the whole warp ----
+// A lane reading ITS row straight from global memory (12 x 128-bit at a 192-byte stride, or 45 scalars at 180 bytes
+// for Frosting's `rest` rows) costs 32 LSU wavefronts per instruction -- two to seven times the sectors the rows
+// occupy -- and that, not arithmetic, bounded this kernel.  Here the warp walks the rows together: each instruction
+// touches one or two rows contiguously (<= 12 sectors); the lanes then work on their rows in shared memory (row stride
+// odd in words / 13 in float4: conflict-free).  `rows` <= 32 rows are live; lane r holds row r's pointer.
+constexpr int kStageStride4 = 13;                    // float4 per staged row (12 used) -- standard path, M == 16
+constexpr int kStageStride = 4 * kStageStride4;      // floats per staged row: 52
+constexpr int kFrostStride = 49;                     // frosting path: 3 dc + 45 rest floats, odd stride
+
+// The loads of a batch are all issued before the first one is consumed (a plain loop would pay one memory round trip
+// per row: load -> store to shared -> next load).
+__device__ __forceinline__ void warp_gather_rows4(const float* my_row, float4* stage4, int rows, int lane) {
+    const int half = lane / 12, k4 = lane - 12 * half;          // lanes 0-11: row 2t, 12-23: row 2t+1, 24-31: idle
+#pragma unroll
+    for (int t0 = 0; t0 < 16; t0 += 8) {
+        if (2 * t0 >= rows) break;
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = 2 * (t0 + u) + half;
+            const float4* p = reinterpret_cast<const float4*>(__shfl_sync(0xffffffffu, (unsigned long long)my_row, r & 31));
+            v[u] = (half < 2 && r < rows) ? __ldg(p + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = 2 * (t0 + u) + half;
+            if (half < 2 && r < rows) stage4[r * kStageStride4 + k4] = v[u];
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_scatter_rows4(float* my_row, const float4* stage4, int rows, int lane) {
+    __syncwarp();
+    const int half = lane / 12, k4 = lane - 12 * half;
+    for (int t = 0; t < (rows + 1) / 2; ++t) {
+        const int r = 2 * t + half;
+        float4* p = reinterpret_cast<float4*>(__shfl_sync(0xffffffffu, (unsigned long long)my_row, r & 31));
+        if (half < 2 && r < rows) p[k4] = stage4[r * kStageStride4 + k4];
+    }
+    __syncwarp();
+}
+
+// 32 CONSECUTIVE rows of 12 float4 (the in-place walk): the block is one contiguous 6 KB span
+__device__ __forceinline__ void warp_gather_block4(const float* block, float4* stage4, int lane) {
+    const float4* src = reinterpret_cast<const float4*>(block);
+    float4 v[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) v[t] = __ldg(src + t * 32 + lane);
+#pragma unroll
+    for (int t = 0; t < 12; ++t) { const int f = t * 32 + lane; stage4[(f / 12) * kStageStride4 + (f % 12)] = v[t]; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_scatter_block4(float* block, const float4* stage4, int lane) {
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(block);
+#pragma unroll
+    for (int t = 0; t < 12; ++t) { const int f = t * 32 + lane; dst[f] = stage4[(f / 12) * kStageStride4 + (f % 12)]; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_gather_rows(const float* my_row, int nf, float* stage, int stride, int rows, int lane) {
+    // nf <= 64 floats per row: two loads per lane and row, sixteen rows in flight
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 16) {
+        if (r0 >= rows) break;
+        float v0[16], v1[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int r = r0 + u;
+            const float* p = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)my_row, r));
+            v0[u] = (r < rows && lane < nf) ? __ldg(p + lane) : 0.f;
+            v1[u] = (r < rows && lane + 32 < nf) ? __ldg(p + lane + 32) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int r = r0 + u;
+            if (r < rows && lane < nf) stage[r * stride + lane] = v0[u];
+            if (r < rows && lane + 32 < nf) stage[r * stride + lane + 32] = v1[u];
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_scatter_rows(float* my_row, int nf, const float* stage, int stride, int rows, int lane) {
+    __syncwarp();
+    for (int r = 0; r < rows; ++r) {
+        float* p = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)my_row, r));
+        for (int k = lane; k < nf; k += 32) p[k] = stage[r * stride + k];
+    }
+    __syncwarp();
+}
+
+// One kernel, two walks over the Gaussians (32 per warp and step):
+//   kList  -- the RENDERED Gaussians only, over the list preprocess appended them to (vis_list, no particular order,
+//             FB200_ST_NUM_VISIBLE entries): full warps whatever the visibility pattern; unrendered rows are never
+//             touched.  The sparse-row contract and frosting mode: ~10 % of a Frosting layer is rendered per camera.
+//   !kList -- in place over all P rows, for the reference's dense contract (zeros for unrendered rows): runs of 32
+//             unrendered rows are zero-filled with coalesced 128-bit stores, the others computed with the unrendered lanes
+//             writing zeros in the same store instructions.  (List walk + a separate zero-fill kernel was measured for
+//             this contract too: C3 0.142 vs 0.163 ms, but C5 0.80 vs 0.64 and C2 0.081 vs 0.070 -- a list step costs
+//             one more dependent memory round trip than an in-place step, which only pays off when most rows are skipped.)
+// SH rows (192 B in, 192 B out per Gaussian) always travel through a per-warp staging block: see the movers above.
+// kFrost (row f1): attributes are rebuilt from Frosting's parameters and the chain rule continues through
+// frosting_attr.cuh to the PARAMETER gradients.
+template <bool kFrost, bool kList>
+__global__ void __launch_bounds__(kGeomThreads, 4)
 geom_bwd_kernel(BwdArgs a) {
     __shared__ float view[16], proj[16], campos[3];
-    __shared__ float4 sh_stage[kGeomThreads / 32][32 * kShRow];
+    __shared__ __align__(16) float stage_all[kGeomThreads / 32][32 * kStageStride];
     if (threadIdx.x < 16) {
         view[threadIdx.x] = a.in.d_viewmatrix[threadIdx.x];
         proj[threadIdx.x] = a.in.d_projmatrix[threadIdx.x];
@@ -91,45 +217,69 @@ geom_bwd_kernel(BwdArgs a) {
     if (threadIdx.x < 3) campos[threadIdx.x] = a.in.d_campos[threadIdx.x];
     __syncthreads();
 
-    const int P = a.prm.P, M = a.prm.sh_coeffs, D = a.prm.sh_degree;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int M = a.prm.sh_coeffs, D = a.prm.sh_degree;
+    const fb200_frosting_params& fr = a.fr;
+    const int n = kList ? a.status[FB200_ST_NUM_VISIBLE] : a.prm.P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g0 = idx - lane;                       // first Gaussian of this warp
-    const bool full_warp = g0 + 31 < P;              // all 32 lanes own a Gaussian
-    const bool in_range = idx < P;
-    const bool visible = in_range && a.radii[idx] > 0;
+    float* const stage = stage_all[warp];
+    float4* const stage4 = reinterpret_cast<float4*>(stage);
+    constexpr int kWarps = kGeomThreads / 32;
+    // a warp takes 32 consecutive entries at a time; the lanes behind the end shadow entry `jb` (valid memory, results
+    // discarded) so that the cooperative row moves stay warp-uniform
+    for (int jb = (blockIdx.x * kWarps + warp) * 32; jb < n; jb += gridDim.x * kWarps * 32) {
+        const int rows = min(32, n - jb);
+        const bool in_rows = lane < rows;
+        int idx;
+        bool active;             // this lane computes a gradient row
+        if (kList) {
+            idx = (int)a.vis_list[jb + (in_rows ? lane : 0)];
+            active = in_rows;
+        } else {
+            idx = jb + (in_rows ? lane : 0);
+            active = in_rows && a.radii[idx] > 0;
+            if (!__any_sync(full, active)) {
+                // nothing rendered in this run (the common case under occlusion culling): zeros, coalesced
+                if (!a.zeroed_elsewhere || rows < 32) {
+                    if (rows == 32) zero_warp_rows(a, (size_t)jb, M, lane);
+                    else if (in_rows) zero_row(a, (size_t)idx, M);
+                }
+                continue;
+            }
+        }
+        const bool write = kList ? active : in_rows;      // this lane owns an output row (zeros if it computed none)
+        const size_t i = (size_t)idx;
 
-    // Warps whose 32 Gaussians are all invisible (culled / masked by occlusion: the common case for a
-    // Frosting layer, where visibility is coherent in face order) only have zeros to write: do it with
-    // fully coalesced 128-bit stores instead of 32 scattered scalar stores per thread.
-    if (full_warp && !__any_sync(0xffffffffu, visible)) {
-        // sparse_rows: the consumer knows radii and never reads these rows (row f1); zero_elsewhere: zero_rows_kernel has
-        // written them, concurrently with the blend backward
-        if (a.g.sparse_rows || a.zeroed_elsewhere) return;
-        zero_warp_rows(a, (size_t)g0, M, lane);
-        return;
-    }
-    const size_t i = (size_t)(in_range ? idx : 0);
-    if (visible && a.in.d_shs != nullptr && M > 0) {
-        // the SH row is read at the very end of a long dependent chain: start it moving now
-        const char* row = reinterpret_cast<const char*>(a.in.d_shs + i * M * 3);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
-        if (M * 12 > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));
-    }
-    // SH gradients of a full warp are staged in shared memory and written out coalesced (M == 16)
-    const bool stage_sh = full_warp && M == 16 && a.g.d_dL_dsh != nullptr;
-    float4* stage = sh_stage[warp] + lane * kShRow;
+        float* dsh = (!kFrost && a.g.d_dL_dsh != nullptr && M > 0) ? a.g.d_dL_dsh + i * M * 3 : nullptr;
+        const bool has_sh = kFrost || (a.in.d_shs != nullptr && M > 0 && dsh != nullptr);
+        const bool staged4 = !kFrost && has_sh && M == 16;
+        // the rows every lane reads for itself further down: start them moving now, beside the staged SH rows
+        auto touch = [](const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); };
+        touch(a.acc + i * 12);
+        if (kFrost) {
+            touch(fr.d_bary_logits + 6 * i); touch(fr.d_cells + i); touch(fr.d_log_scales + 3 * i);
+            touch(fr.d_quats + 4 * i); touch(fr.d_opacity_logits + i);
+        } else {
+            touch(a.in.d_means3D + 3 * i);
+            if (a.in.d_scales) { touch(a.in.d_scales + 3 * i); touch(a.in.d_rotations + 4 * i); }
+        }
+        if (kFrost) {
+            // dc | rest rows into the staging block: [0..2] dc, [3..] rest
+            warp_gather_rows(fr.d_sh_rest + i * (size_t)fr.sh_rest * 3, fr.sh_rest * 3, stage + 3, kFrostStride, rows, lane);
+            stage[lane * kFrostStride + 0] = __ldg(fr.d_sh_dc + 3 * i);
+            stage[lane * kFrostStride + 1] = __ldg(fr.d_sh_dc + 3 * i + 1);
+            stage[lane * kFrostStride + 2] = __ldg(fr.d_sh_dc + 3 * i + 2);
+        } else if (staged4) {
+            if (!kList && rows == 32) warp_gather_block4(a.in.d_shs + (size_t)jb * 48, stage4, lane);
+            else warp_gather_rows4(a.in.d_shs + i * 48, stage4, rows, lane);
+        }
 
-    float g_mean2d_x = 0.f, g_mean2d_y = 0.f, g_op = 0.f;
-    V3 g_col = v3(0.f, 0.f, 0.f), g_mean = v3(0.f, 0.f, 0.f);
-    float g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    V3 g_scale = v3(0.f, 0.f, 0.f);
-    float4 g_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+        float g_mean2d_x, g_mean2d_y, g_op;
+        V3 g_col, g_mean;
+        float g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        V3 g_scale = v3(0.f, 0.f, 0.f);
+        float4 g_rot = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float* dsh = (a.g.d_dL_dsh != nullptr && M > 0) ? a.g.d_dL_dsh + i * M * 3 : nullptr;
-    const bool has_sh = a.in.d_shs != nullptr && M > 0 && dsh != nullptr;
-
-    if (visible) {
         const float4* accp = reinterpret_cast<const float4*>(a.acc + i * 12);
         const float4 a0 = accp[0], a1 = accp[1];
         const float a2x = a.acc[i * 12 + 8];
@@ -138,17 +288,30 @@ geom_bwd_kernel(BwdArgs a) {
         g_op = a1.y;
         g_col = v3(a1.z, a1.w, a2x);
 
-        const float mx = a.in.d_means3D[3 * i], my = a.in.d_means3D[3 * i + 1], mz = a.in.d_means3D[3 * i + 2];
+        // frosting mode: position, scale, rotation from the parameters (bit-identical to the forward's)
+        float fw[6], q_nrm = 1.f, raw_s[3] = {0.f, 0.f, 0.f};
+        int fvid[3];
+        float mx, my, mz;
+        if (kFrost) frost_point(fr, i, fw, fvid, mx, my, mz);
+        else { mx = a.in.d_means3D[3 * i]; my = a.in.d_means3D[3 * i + 1]; mz = a.in.d_means3D[3 * i + 2]; }
 
         // ---- 3D covariance (recomputed from scale/rotation, or the precomputed input) ----
         float S[6];
         float sx = 0.f, sy = 0.f, sz = 0.f, qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
         float Rm[3][3];   // Rm[row][col], maths convention: Sigma = Rm^T diag(s)^2 Rm
-        const bool from_sr = a.in.d_cov3D_precomp == nullptr;
+        const bool from_sr = kFrost || a.in.d_cov3D_precomp == nullptr;
         if (from_sr) {
             const float mod = a.prm.scale_modifier;
-            sx = mod * a.in.d_scales[3 * i]; sy = mod * a.in.d_scales[3 * i + 1]; sz = mod * a.in.d_scales[3 * i + 2];
-            const float4 q = reinterpret_cast<const float4*>(a.in.d_rotations)[i];
+            float4 q;
+            if (kFrost) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) raw_s[k] = expf(__ldg(fr.d_log_scales + 3 * i + k));
+                q = frost_normalize(__ldg(reinterpret_cast<const float4*>(fr.d_quats) + i), q_nrm);
+            } else {
+                raw_s[0] = a.in.d_scales[3 * i]; raw_s[1] = a.in.d_scales[3 * i + 1]; raw_s[2] = a.in.d_scales[3 * i + 2];
+                q = reinterpret_cast<const float4*>(a.in.d_rotations)[i];
+            }
+            sx = mod * raw_s[0]; sy = mod * raw_s[1]; sz = mod * raw_s[2];
             qr = q.x; qx = q.y; qy = q.z; qz = q.w;
             Rm[0][0] = 1.f - 2.f * (qy * qy + qz * qz); Rm[0][1] = 2.f * (qx * qy + qr * qz); Rm[0][2] = 2.f * (qx * qz - qr * qy);
             Rm[1][0] = 2.f * (qx * qy - qr * qz); Rm[1][1] = 1.f - 2.f * (qx * qx + qz * qz); Rm[1][2] = 2.f * (qy * qz + qr * qx);
@@ -228,7 +391,6 @@ geom_bwd_kernel(BwdArgs a) {
             const V3 dorig = v3(mx - campos[0], my - campos[1], mz - campos[2]);
             const float len = sqrtf(dot(dorig, dorig));
             const float x = dorig.x / len, y = dorig.y / len, z = dorig.z / len;
-            const float* sh = a.in.d_shs + i * M * 3;
             // basis value and gradient per coefficient
             float bv[16], bx[16], by[16], bz[16];
 #pragma unroll
@@ -257,19 +419,34 @@ geom_bwd_kernel(BwdArgs a) {
                 }
             }
             const int ncoef = (D + 1) * (D + 1);
-            V3 dcdx = v3(0.f, 0.f, 0.f), dcdy = v3(0.f, 0.f, 0.f), dcdz = v3(0.f, 0.f, 0.f);
             const float dR[3] = {dRGB.x, dRGB.y, dRGB.z};
             float ax[3] = {0.f, 0.f, 0.f}, ay[3] = {0.f, 0.f, 0.f}, az[3] = {0.f, 0.f, 0.f};
-            if (M == 16) {
-                // 192 B per Gaussian in and out: twelve 128-bit loads and stores instead of 48 + 48
-                // scalar accesses at a 192-byte lane stride (those were LSU-bound).
-                const float4* sh4 = reinterpret_cast<const float4*>(sh);
-                float4* dsh4 = reinterpret_cast<float4*>(dsh);
+            if (kFrost) {
+                // dc | rest values from the staging block; their gradients overwrite them there
+                float* srow = stage + lane * kFrostStride;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < M) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float o = 0.f;
+                            if (k < ncoef) {
+                                const float sv = srow[3 * k + c];
+                                o = bv[k] * dR[c];
+                                ax[c] += bx[k] * sv; ay[c] += by[k] * sv; az[c] += bz[k] * sv;
+                            }
+                            srow[3 * k + c] = o;
+                        }
+                    }
+                }
+            } else if (M == 16) {
+                // 192 B per Gaussian in and out, through the staging block (filled above, written back below)
+                float4* srow4 = stage4 + lane * kStageStride4;
 #pragma unroll
                 for (int q = 0; q < 12; ++q) {
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
                     if (4 * q < 3 * ncoef) {
-                        const float4 s4 = __ldg(sh4 + q);
+                        const float4 s4 = srow4[q];
                         const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -280,27 +457,29 @@ geom_bwd_kernel(BwdArgs a) {
                             }
                         }
                     }
-                    if (stage_sh) stage[q] = make_float4(o[0], o[1], o[2], o[3]);
-                    else dsh4[q] = make_float4(o[0], o[1], o[2], o[3]);
+                    srow4[q] = make_float4(o[0], o[1], o[2], o[3]);
                 }
             } else {
+                const float* sh = a.in.d_shs + i * M * 3;
                 for (int k = 0; k < M; ++k) {
                     float o0 = 0.f, o1 = 0.f, o2 = 0.f;
                     if (k < ncoef && k < 16) {
                         float bvk = 0.f, bxk = 0.f, byk = 0.f, bzk = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j == k) { bvk = bv[j]; bxk = bx[j]; byk = by[j]; bzk = bz[j]; }
+                        for (int j2 = 0; j2 < 16; ++j2)
+                            if (j2 == k) { bvk = bv[j2]; bxk = bx[j2]; byk = by[j2]; bzk = bz[j2]; }
                         o0 = bvk * dR[0]; o1 = bvk * dR[1]; o2 = bvk * dR[2];
                         const float s0 = sh[3 * k], s1 = sh[3 * k + 1], s2 = sh[3 * k + 2];
                         ax[0] += bxk * s0; ax[1] += bxk * s1; ax[2] += bxk * s2;
                         ay[0] += byk * s0; ay[1] += byk * s1; ay[2] += byk * s2;
                         az[0] += bzk * s0; az[1] += bzk * s1; az[2] += bzk * s2;
                     }
-                    dsh[3 * k] = o0; dsh[3 * k + 1] = o1; dsh[3 * k + 2] = o2;
+                    if (write) {
+                        dsh[3 * k] = active ? o0 : 0.f; dsh[3 * k + 1] = active ? o1 : 0.f; dsh[3 * k + 2] = active ? o2 : 0.f;
+                    }
                 }
             }
-            dcdx = v3(ax[0], ax[1], ax[2]); dcdy = v3(ay[0], ay[1], ay[2]); dcdz = v3(az[0], az[1], az[2]);
+            const V3 dcdx = v3(ax[0], ax[1], ax[2]), dcdy = v3(ay[0], ay[1], ay[2]), dcdz = v3(az[0], az[1], az[2]);
             // through dir = dorig / |dorig|:  d/dv = (dv |v|^2 - v (v . dv)) / |v|^3
             const V3 ddir = v3(dot(dcdx, dRGB), dot(dcdy, dRGB), dot(dcdz, dRGB));
             const float sum2 = dot(dorig, dorig);
@@ -309,7 +488,27 @@ geom_bwd_kernel(BwdArgs a) {
             g_mean.x += (ddir.x * sum2 - dorig.x * vd) * inv32;
             g_mean.y += (ddir.y * sum2 - dorig.y * vd) * inv32;
             g_mean.z += (ddir.z * sum2 - dorig.z * vd) * inv32;
+        } else if (dsh != nullptr && write) {
+            for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
         }
+        // SH gradient rows back to memory, by the whole warp (has_sh and M are warp-uniform)
+        if (!kList && staged4 && !active) {
+            // in-place walk: an unrendered lane's staged row holds whatever the garbage inputs produced: zeros go out
+#pragma unroll
+            for (int q = 0; q < 12; ++q) stage4[lane * kStageStride4 + q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (kFrost) {
+            warp_scatter_rows(a.fg.d_sh_rest + i * (size_t)fr.sh_rest * 3, fr.sh_rest * 3, stage + 3, kFrostStride, rows, lane);
+            if (active) {
+                a.fg.d_sh_dc[3 * i] = stage[lane * kFrostStride]; a.fg.d_sh_dc[3 * i + 1] = stage[lane * kFrostStride + 1];
+                a.fg.d_sh_dc[3 * i + 2] = stage[lane * kFrostStride + 2];
+            }
+            __syncwarp();
+        } else if (staged4) {
+            if (!kList && rows == 32) warp_scatter_block4(a.g.d_dL_dsh + (size_t)jb * 48, stage4, lane);
+            else warp_scatter_rows4(dsh, stage4, rows, lane);
+        }
+        if (!write) continue;
 
         // ---- cov3D -> scale, quaternion ----
         if (from_sr) {
@@ -338,47 +537,50 @@ geom_bwd_kernel(BwdArgs a) {
             g_rot.z = 2.f * qx * (Hm[1][0] + Hm[0][1]) + 2.f * qr * (Hm[2][0] - Hm[0][2]) + 2.f * qz * (Hm[1][2] + Hm[2][1]) - 4.f * qy * (Hm[2][2] + Hm[0][0]);
             g_rot.w = 2.f * qr * (Hm[0][1] - Hm[1][0]) + 2.f * qx * (Hm[2][0] + Hm[0][2]) + 2.f * qy * (Hm[1][2] + Hm[2][1]) - 4.f * qz * (Hm[1][1] + Hm[0][0]);
         }
-    }
-    if ((!visible || !has_sh) && dsh != nullptr && in_range) {
-        if (M == 16) {
-            float4* dsh4 = reinterpret_cast<float4*>(dsh);
-#pragma unroll
-            for (int q = 0; q < 12; ++q) {
-                if (stage_sh) stage[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                else dsh4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else {
-            for (int k = 0; k < M * 3; ++k) dsh[k] = 0.f;
-        }
-    }
-    if (stage_sh) {
-        __syncwarp();
-        float4* out4 = reinterpret_cast<float4*>(a.g.d_dL_dsh + (size_t)48 * g0);
-        const float4* rows = sh_stage[warp];
-#pragma unroll
-        for (int r = 0; r < 12; ++r) {
-            const int f = r * 32 + lane;            // float4 index within the warp's 6 KB block
-            out4[f] = rows[(f / 12) * kShRow + (f % 12)];
-        }
-    }
-    if (!in_range) return;
 
-    a.g.d_dL_dmeans2D[3 * i] = g_mean2d_x; a.g.d_dL_dmeans2D[3 * i + 1] = g_mean2d_y; a.g.d_dL_dmeans2D[3 * i + 2] = 0.f;
-    if (a.g.d_dL_dcolors) { a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z; }
-    a.g.d_dL_dopacity[i] = g_op;
-    a.g.d_dL_dmeans3D[3 * i] = g_mean.x; a.g.d_dL_dmeans3D[3 * i + 1] = g_mean.y; a.g.d_dL_dmeans3D[3 * i + 2] = g_mean.z;
-    if (a.g.d_dL_dcov3D)
-        for (int k = 0; k < 6; ++k) a.g.d_dL_dcov3D[6 * i + k] = g_cov[k];
-    if (a.g.d_dL_dscales) { a.g.d_dL_dscales[3 * i] = g_scale.x; a.g.d_dL_dscales[3 * i + 1] = g_scale.y; a.g.d_dL_dscales[3 * i + 2] = g_scale.z; }
-    if (a.g.d_dL_drotations) reinterpret_cast<float4*>(a.g.d_dL_drotations)[i] = g_rot;
+        if (!kList && !active) {
+            // in-place walk, unrendered row inside a run that has rendered ones: whatever its garbage inputs produced is
+            // dropped, zeros go out through the same stores
+            g_mean2d_x = 0.f; g_mean2d_y = 0.f; g_op = 0.f;
+            g_col = v3(0.f, 0.f, 0.f); g_mean = v3(0.f, 0.f, 0.f); g_scale = v3(0.f, 0.f, 0.f);
+            g_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) g_cov[k] = 0.f;
+        }
+        if (a.g.d_dL_dmeans2D) {
+            a.g.d_dL_dmeans2D[3 * i] = g_mean2d_x; a.g.d_dL_dmeans2D[3 * i + 1] = g_mean2d_y; a.g.d_dL_dmeans2D[3 * i + 2] = 0.f;
+        }
+        if (kFrost) {
+            // the chain rule through the attribute maps (fb200_frosting_attributes_backward, same formulas)
+            float gb[6];
+            frost_point_backward(fr, fw, fvid, g_mean.x, g_mean.y, g_mean.z, a.fg.d_inner_verts, a.fg.d_outer_verts, gb);
+            float2* gb2 = reinterpret_cast<float2*>(a.fg.d_bary_logits + 6 * i);
+            gb2[0] = make_float2(gb[0], gb[1]); gb2[1] = make_float2(gb[2], gb[3]); gb2[2] = make_float2(gb[4], gb[5]);
+            const float sg = frost_sigmoid(__ldg(fr.d_opacity_logits + i));
+            a.fg.d_opacity_logits[i] = g_op * sg * (1.0f - sg);
+            a.fg.d_log_scales[3 * i] = g_scale.x * raw_s[0];
+            a.fg.d_log_scales[3 * i + 1] = g_scale.y * raw_s[1];
+            a.fg.d_log_scales[3 * i + 2] = g_scale.z * raw_s[2];
+            reinterpret_cast<float4*>(a.fg.d_quats)[i] =
+                frost_normalize_backward(make_float4(qr, qx, qy, qz), q_nrm, g_rot);
+        } else {
+            if (a.g.d_dL_dcolors) { a.g.d_dL_dcolors[3 * i] = g_col.x; a.g.d_dL_dcolors[3 * i + 1] = g_col.y; a.g.d_dL_dcolors[3 * i + 2] = g_col.z; }
+            a.g.d_dL_dopacity[i] = g_op;
+            a.g.d_dL_dmeans3D[3 * i] = g_mean.x; a.g.d_dL_dmeans3D[3 * i + 1] = g_mean.y; a.g.d_dL_dmeans3D[3 * i + 2] = g_mean.z;
+            if (a.g.d_dL_dcov3D)
+                for (int k = 0; k < 6; ++k) a.g.d_dL_dcov3D[6 * i + k] = g_cov[k];
+            if (a.g.d_dL_dscales) { a.g.d_dL_dscales[3 * i] = g_scale.x; a.g.d_dL_dscales[3 * i + 1] = g_scale.y; a.g.d_dL_dscales[3 * i + 2] = g_scale.z; }
+            if (a.g.d_dL_drotations) reinterpret_cast<float4*>(a.g.d_dL_drotations)[i] = g_rot;
+        }
+    }
 }
 
 }  // namespace
 
 cudaError_t launch_zero_rows(const BwdArgs& a, cudaStream_t s) {
     if (a.prm.P >= 32) {
-        // HBM-bound stores: one small CTA per SM keeps HBM busy without taking the blend backward's warp slots
-        zero_rows_kernel<<<148, 128, 0, s>>>(a);
+        // HBM-bound stores beside the blend backward: one CTA per SM keeps HBM busy without taking that kernel's warp slots
+        zero_rows_kernel<<<148, 256, 0, s>>>(a);
         count_launch();
     }
     return cudaGetLastError();
@@ -386,7 +588,22 @@ cudaError_t launch_zero_rows(const BwdArgs& a, cudaStream_t s) {
 
 cudaError_t launch_geom_bwd(const BwdArgs& a, cudaStream_t s) {
     if (a.prm.P > 0) {
-        geom_bwd_kernel<<<(a.prm.P + kGeomThreads - 1) / kGeomThreads, kGeomThreads, 0, s>>>(a);
+        // grid-stride, four resident CTAs per SM (the visible list's length is known to the device only)
+        const int want = (a.prm.P + kGeomThreads - 1) / kGeomThreads;
+        const int blocks = want < 148 * 4 ? want : 148 * 4;
+        if (a.frosting) {
+            if (a.fg.d_inner_verts != nullptr && a.fr.n_verts > 0) {
+                cudaError_t e = cudaMemsetAsync(a.fg.d_inner_verts, 0, sizeof(float) * 3 * (size_t)a.fr.n_verts, s);
+                if (e != cudaSuccess) return e;
+                e = cudaMemsetAsync(a.fg.d_outer_verts, 0, sizeof(float) * 3 * (size_t)a.fr.n_verts, s);
+                if (e != cudaSuccess) return e;
+            }
+            geom_bwd_kernel<true, true><<<blocks, kGeomThreads, 0, s>>>(a);
+        } else if (a.g.sparse_rows) {
+            geom_bwd_kernel<false, true><<<blocks, kGeomThreads, 0, s>>>(a);
+        } else {
+            geom_bwd_kernel<false, false><<<blocks, kGeomThreads, 0, s>>>(a);
+        }
         count_launch();
     }
     return cudaGetLastError();

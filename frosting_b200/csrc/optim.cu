@@ -41,37 +41,79 @@ __device__ __forceinline__ float adam1(float g, float& m, float& v, float p, flo
     return p - lr_over_bc1 * (m / denom);
 }
 
+__device__ __forceinline__ void mc_st(float4* p, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // kPeers: compile-time bound on `world` (1, 2, 4, 8) so that small boxes do not pay registers for eight gradient
-// vectors -- more resident warps = more remote loads in flight, which is what hides the NVLink latency
-template <int kPeers>
-__global__ void __launch_bounds__(256, kPeers <= 4 ? 4 : 3)
+// vectors -- more resident warps = more remote loads in flight, which is what hides the NVLink latency.
+// kMasked: sparse gradient rows (fb200_adam_args.peer_row_radii): a peer's vector is fetched only if one of its (at
+// most four) rows was rendered on that peer, and the elements of its other rows -- unwritten memory -- are dropped.
+template <int kPeers, bool kMasked>
+__global__ void __launch_bounds__(256, kMasked ? (kPeers <= 2 ? 4 : 2) : (kPeers <= 4 ? 4 : 3))
 adam_shard_kernel(const fb200_adam_args a) {
     const int64_t v_lo = a.shard_lo >> 2, v_hi = a.shard_hi >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float4* __restrict__ mom1 = reinterpret_cast<float4*>(a.d_exp_avg);
     float4* __restrict__ mom2 = reinterpret_cast<float4*>(a.d_exp_avg_sq);
+    float4* mc_p = reinterpret_cast<float4*>(a.mc_params);
     // torch forms 1 - beta in double and rounds once (python floats); (float)1 - (float)beta would be off by 1e-5 relative
     const Coef c{(float)(1.0 - a.beta1), (float)a.beta2, (float)(1.0 - a.beta2), a.bias_correction2_sqrt, a.eps};
     for (int64_t i = v_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v_hi; i += stride) {
+        // group of this vector (group starts are multiples of 4 elements, so a vector never straddles two)
+        const int64_t e = i << 2;
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < FB200_ADAM_MAX_GROUPS; ++j)
+            if (j < a.n_groups && e >= a.group_start[j]) k = j;
+        const float lr = a.lr[k];
+        if (lr < 0.f) continue;        // group without a gradient this step: untouched, like a torch parameter with .grad None
+        const float step = lr / a.bias_correction1;
+
         // gradient: one 128-bit load per peer, all issued before the first use
         float4 g[kPeers];
+        const uint32_t w = kMasked ? (uint32_t)a.row_width[k] : 0u;
+        if (kMasked && w > 0) {
+            const uint32_t off = (uint32_t)(e - a.group_start[k]);
+            const uint32_t last = (uint32_t)a.row_count - 1u;      // padding elements behind the last row map onto it
+            uint32_t r = off / w, rem = off - r * w;
+            uint32_t rows[4];
 #pragma unroll
-        for (int p = 0; p < kPeers; ++p)
-            if (p < a.world) g[p] = ld_stream(reinterpret_cast<const float4*>(a.peer_grads[p]) + i);
+            for (int j = 0; j < 4; ++j) {
+                rows[j] = min(r, last);
+                if (++rem == w) { rem = 0; ++r; }
+            }
+            bool live[kPeers][4];
+#pragma unroll
+            for (int p = 0; p < kPeers; ++p) {
+                if (p < a.world) {
+                    const int32_t* rr = a.peer_row_radii[p];
+                    live[p][0] = __ldcg(rr + rows[0]) > 0;
+                    live[p][3] = rows[3] == rows[0] ? live[p][0] : __ldcg(rr + rows[3]) > 0;
+                    // four consecutive elements span at most two rows unless rows are shorter than 3 elements
+                    live[p][1] = rows[1] == rows[0] ? live[p][0] : (rows[1] == rows[3] ? live[p][3] : __ldcg(rr + rows[1]) > 0);
+                    live[p][2] = rows[2] == rows[0] ? live[p][0] : (rows[2] == rows[3] ? live[p][3] : __ldcg(rr + rows[2]) > 0);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < kPeers; ++p) {
+                g[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p < a.world && (live[p][0] || live[p][1] || live[p][2] || live[p][3])) {
+                    const float4 t = ld_stream(reinterpret_cast<const float4*>(a.peer_grads[p]) + i);
+                    g[p] = make_float4(live[p][0] ? t.x : 0.f, live[p][1] ? t.y : 0.f, live[p][2] ? t.z : 0.f, live[p][3] ? t.w : 0.f);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPeers; ++p)
+                if (p < a.world) g[p] = ld_stream(reinterpret_cast<const float4*>(a.peer_grads[p]) + i);
+        }
         float4 s = g[0];
 #pragma unroll
         for (int p = 1; p < kPeers; ++p)
             if (p < a.world) { s.x += g[p].x; s.y += g[p].y; s.z += g[p].z; s.w += g[p].w; }
         s.x *= a.grad_scale; s.y *= a.grad_scale; s.z *= a.grad_scale; s.w *= a.grad_scale;
-
-        // group of this vector (group starts are multiples of 4 elements, so a vector never straddles two)
-        const int64_t e = i << 2;
-        float lr = a.lr[0];
-#pragma unroll
-        for (int k = 1; k < FB200_ADAM_MAX_GROUPS; ++k)
-            if (k < a.n_groups && e >= a.group_start[k]) lr = a.lr[k];
-        if (lr < 0.f) continue;        // group without a gradient this step: untouched, like a torch parameter with .grad None
-        const float step = lr / a.bias_correction1;
 
         const int64_t li = i - v_lo;
         float4 m = mom1[li], v = mom2[li];
@@ -82,9 +124,13 @@ adam_shard_kernel(const fb200_adam_args a) {
         p.w = adam1(s.w, m.w, v.w, p.w, step, c);
         mom1[li] = m;
         mom2[li] = v;
+        if (kMasked && mc_p != nullptr) {
+            mc_st(mc_p + i, p);           // the switch writes every replica
+        } else {
 #pragma unroll
-        for (int q = 0; q < kPeers; ++q)
-            if (q < a.world) __stcg(reinterpret_cast<float4*>(a.peer_params[q]) + i, p);
+            for (int q = 0; q < kPeers; ++q)
+                if (q < a.world) __stcg(reinterpret_cast<float4*>(a.peer_params[q]) + i, p);
+        }
     }
 }
 
@@ -97,10 +143,6 @@ __device__ __forceinline__ float4 mc_ld_reduce(const float4* p) {
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void mc_st(float4* p, const float4& v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -146,11 +188,18 @@ cudaError_t launch_adam_shard(const fb200_adam_args& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (vecs + 255) / 256;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);   // 8 resident CTAs of 256 threads per SM
-    if (a.world > 1 && a.mc_grads && a.mc_params) adam_shard_mc_kernel<<<grid, 256, 0, s>>>(a);
-    else if (a.world == 1) adam_shard_kernel<1><<<grid, 256, 0, s>>>(a);
-    else if (a.world == 2) adam_shard_kernel<2><<<grid, 256, 0, s>>>(a);
-    else if (a.world <= 4) adam_shard_kernel<4><<<grid, 256, 0, s>>>(a);
-    else adam_shard_kernel<8><<<grid, 256, 0, s>>>(a);
+    if (a.peer_row_radii[0] != nullptr) {
+        // sparse gradient rows: masked peer loads (the in-switch sum would read the unwritten rows), multicast store if mapped
+        if (a.world == 1) adam_shard_kernel<1, true><<<grid, 256, 0, s>>>(a);
+        else if (a.world == 2) adam_shard_kernel<2, true><<<grid, 256, 0, s>>>(a);
+        else if (a.world <= 4) adam_shard_kernel<4, true><<<grid, 256, 0, s>>>(a);
+        else adam_shard_kernel<8, true><<<grid, 256, 0, s>>>(a);
+    }
+    else if (a.world > 1 && a.mc_grads && a.mc_params) adam_shard_mc_kernel<<<grid, 256, 0, s>>>(a);
+    else if (a.world == 1) adam_shard_kernel<1, false><<<grid, 256, 0, s>>>(a);
+    else if (a.world == 2) adam_shard_kernel<2, false><<<grid, 256, 0, s>>>(a);
+    else if (a.world <= 4) adam_shard_kernel<4, false><<<grid, 256, 0, s>>>(a);
+    else adam_shard_kernel<8, false><<<grid, 256, 0, s>>>(a);
     count_launch();
     return cudaGetLastError();
 }

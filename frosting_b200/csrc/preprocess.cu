@@ -19,6 +19,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "frosting_attr.cuh"
 
 namespace fb200 {
 
@@ -128,16 +129,13 @@ __device__ __forceinline__ uint32_t rect_coord(float v, uint32_t g) {
     return min(g, (uint32_t)i);
 }
 
-// computeColorFromSH, forward.cu:20-71.  Returns result before the +0.5 / clamp.
+// The SH row of one Gaussian into registers: 3*M floats, coefficient-major, RGB innermost.
 template <bool kAligned>
-__device__ __forceinline__ void eval_sh(int deg, const float* __restrict__ sh, float x, float y, float z,
-                                        float& o0, float& o1, float& o2) {
-    // sh: 3*M floats, coefficient-major, RGB innermost
-    float c[48];
-    int ncoef = (deg + 1) * (deg + 1);
+__device__ __forceinline__ void load_sh(int deg, const float* __restrict__ sh, float* c) {
+    const int ncoef = (deg + 1) * (deg + 1);
     if (kAligned) {
         const float4* s4 = reinterpret_cast<const float4*>(sh);
-        int nq = (ncoef * 3 + 3) >> 2;
+        const int nq = (ncoef * 3 + 3) >> 2;
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
             if (i < nq) {
@@ -150,6 +148,22 @@ __device__ __forceinline__ void eval_sh(int deg, const float* __restrict__ sh, f
         for (int i = 0; i < 48; ++i)
             if (i < ncoef * 3) c[i] = __ldg(sh + i);
     }
+}
+
+// frosting mode: the same row read in place from its two parameter tensors, dc [P,1,3] | rest [P,M-1,3]
+// (sh_coordinates = cat(dc, rest), frosting_model.py:733-734); rest rows are 12*(M-1) bytes apart: scalar loads
+__device__ __forceinline__ void load_sh_split(int deg, const float* __restrict__ dc, const float* __restrict__ rest,
+                                              float* c) {
+    const int ncoef = (deg + 1) * (deg + 1);
+    c[0] = __ldg(dc); c[1] = __ldg(dc + 1); c[2] = __ldg(dc + 2);
+#pragma unroll
+    for (int i = 3; i < 48; ++i)
+        if (i < ncoef * 3) c[i] = __ldg(rest + i - 3);
+}
+
+// computeColorFromSH, forward.cu:20-71.  Returns result before the +0.5 / clamp.
+__device__ __forceinline__ void eval_sh(int deg, const float* c, float x, float y, float z,
+                                        float& o0, float& o1, float& o2) {
     float r0 = fmul(c[0], kC0), r1 = fmul(c[1], kC0), r2 = fmul(c[2], kC0);
     if (deg > 0) {
         float k;
@@ -202,182 +216,29 @@ struct CamConst {
     float campos[3];
 };
 
-__global__ void __launch_bounds__(256, 4)
-preprocess_fwd_kernel(FwdArgs a) {
-    __shared__ CamConst cam;
-    if (threadIdx.x < 16) {
-        cam.view[threadIdx.x] = a.in.d_viewmatrix[threadIdx.x];
-        cam.proj[threadIdx.x] = a.in.d_projmatrix[threadIdx.x];
-    }
-    if (threadIdx.x < 3) cam.campos[threadIdx.x] = a.in.d_campos[threadIdx.x];
-    __syncthreads();
+#ifndef FB200_PRE_CTAS
+#define FB200_PRE_CTAS 4
+#endif
+constexpr int kPreThreads = 256;
+constexpr int kPreRounds = 1;        // one round: a longer span only serialises runs of survivors inside a few CTAs
+constexpr int kPreSpan = kPreThreads * kPreRounds;     // Gaussians per CTA
 
-    const int P = a.prm.P;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = tid < P;          // no early exit: the tile counting at the end is warp-cooperative
-    const int idx = valid ? tid : P - 1;
-
-    const float* __restrict__ v = cam.view;
-    const float* __restrict__ m = cam.proj;
-
-    // the occlusion inputs first: the cell -> visible-face gather is a dependent chain of its own, started before the
-    // position loads so that the two chains overlap (a culled Gaussian then costs two memory round trips, not three)
-    const bool by_face = a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points;
-    const long long cell = by_face ? __ldg(a.in.d_point_cells + idx) : 0;
-    const uint8_t vis_in = a.in.d_visibility != nullptr ? __ldg(a.in.d_visibility + idx) : (uint8_t)1;
-    const float px = __ldg(a.in.d_means3D + 3 * (size_t)idx + 0);
-    const float py = __ldg(a.in.d_means3D + 3 * (size_t)idx + 1);
-    const float pz = __ldg(a.in.d_means3D + 3 * (size_t)idx + 2);
-    const uint8_t face_in = by_face ? __ldg(a.in.d_face_visible + cell) : (uint8_t)1;
-
-    // in_frustum: keep iff !(p_view.z <= 0.2f)
-    const float depth = affine_row(v, 2, px, py, pz);
-    bool keep = valid && !(depth <= 0.2f);
-    if (valid && !keep && a.prm.prefiltered) {
-        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-        __trap();
-    }
-    // occlusion culling: a per-Gaussian mask tensor, or -- without one -- render_mask = face_visible[_point_cell_indices]
-    // for the mesh-bound Gaussians, True for the trailing background ones (frosting_model.py:1564-1576), looked up in place
-    if (vis_in == 0 || face_in == 0) keep = false;
-    if (keep && a.in.d_shs != nullptr) {
-        // the SH row (192 B at degree 3) is consumed last, after a chain of dependent loads; start it moving now
-        const char* row = reinterpret_cast<const char*>(a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
-        if (a.prm.sh_coeffs * 12 > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));
-    }
-
-    int radius = 0;
-    uint2 rect = make_uint2(0u, 0u);
-
-    if (keep) {
-        const float hx = affine_row(m, 0, px, py, pz);
-        const float hy = affine_row(m, 1, px, py, pz);
-        const float hw = affine_row(m, 3, px, py, pz);
-        const float p_w = __frcp_rn(fadd(hw, 0.0000001f));
-        const float projx = fmul(hx, p_w);
-        const float projy = fmul(hy, p_w);
-
-        Cov3 S;
-        if (a.in.d_cov3D_precomp != nullptr) {
-            const float* c = a.in.d_cov3D_precomp + 6 * (size_t)idx;
-            S.c0 = __ldg(c + 0); S.c1 = __ldg(c + 1); S.c2 = __ldg(c + 2);
-            S.c3 = __ldg(c + 3); S.c4 = __ldg(c + 4); S.c5 = __ldg(c + 5);
-        } else {
-            const float* sc = a.in.d_scales + 3 * (size_t)idx;
-            const float4 q = __ldg(reinterpret_cast<const float4*>(a.in.d_rotations) + idx);
-            S = cov3d_from_scale_rot(__ldg(sc), __ldg(sc + 1), __ldg(sc + 2), a.prm.scale_modifier, q.x, q.y, q.z, q.w);
-        }
-
-        const float3 cov = cov2d(px, py, pz, a.focal_x, a.focal_y, a.prm.tanfovx, a.prm.tanfovy, S, v);
-        const float det = ffma(cov.x, cov.z, -fmul(cov.y, cov.y));
-        if (!(det == 0.0f)) {
-            const float det_inv = __frcp_rn(det);
-            const float conic_x = fmul(cov.z, det_inv);
-            const float conic_y = fmul(cov.y, -det_inv);
-            const float conic_z = fmul(cov.x, det_inv);
-            const float mid = fmul(fadd(cov.x, cov.z), 0.5f);
-            const float sq = __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f));
-            const float lambda1 = fadd(mid, sq);
-            const float lambda2 = fadd(mid, -sq);
-            const float rad_f = fmul(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.0f);
-            const int my_radius = __float2int_ru(rad_f);
-            const float Rf = (float)my_radius;
-            const float pix_x = ndc2pix(projx, a.prm.image_width);
-            const float pix_y = ndc2pix(projy, a.prm.image_height);
-            // getRect, auxiliary.h:46-56
-            const uint32_t gx = (uint32_t)a.tiles_x, gy = (uint32_t)a.tiles_y;
-            const uint32_t minx = rect_coord(fadd(pix_x, -Rf), gx);
-            const uint32_t miny = rect_coord(fadd(pix_y, -Rf), gy);
-            const uint32_t maxx = rect_coord(fadd(fadd(fadd(pix_x, Rf), 16.0f), -1.0f), gx);
-            const uint32_t maxy = rect_coord(fadd(fadd(fadd(pix_y, Rf), 16.0f), -1.0f), gy);
-            const uint32_t touched = (maxx - minx) * (maxy - miny);
-            if (touched != 0) {
-                radius = my_radius;
-                rect = make_uint2(minx | (miny << 16), maxx | (maxy << 16));
-
-                float cr, cg, cb;
-                uint8_t clamp_bits = 0;
-                if (a.in.d_colors_precomp == nullptr) {
-                    // direction = (p - campos) / |p - campos|   (glm::length = sqrt(dot))
-                    const float dx = fadd(-cam.campos[0], px);
-                    const float dy = fadd(-cam.campos[1], py);
-                    const float dz = fadd(-cam.campos[2], pz);
-                    const float len = __fsqrt_rn(dot3x(dx, dx, dy, dy, dz, dz));
-                    const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
-                    const float* sh = a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3;
-                    float r0, r1, r2;
-                    if ((a.prm.sh_coeffs & 3) == 0)
-                        eval_sh<true>(a.prm.sh_degree, sh, x, y, z, r0, r1, r2);
-                    else
-                        eval_sh<false>(a.prm.sh_degree, sh, x, y, z, r0, r1, r2);
-                    // result += 0.5; clamped = result < 0; result = max(result, 0)
-                    const float s0 = fadd(r0, 0.5f), s1 = fadd(r1, 0.5f), s2 = fadd(r2, 0.5f);
-                    clamp_bits = (s0 < 0.f ? 1 : 0) | (s1 < 0.f ? 2 : 0) | (s2 < 0.f ? 4 : 0);
-                    cr = (s0 < 0.f) ? 0.f : s0;
-                    cg = (s1 < 0.f) ? 0.f : s1;
-                    cb = (s2 < 0.f) ? 0.f : s2;
-                } else {
-                    const float* c = a.in.d_colors_precomp + 3 * (size_t)idx;
-                    cr = __ldg(c); cg = __ldg(c + 1); cb = __ldg(c + 2);
-                }
-                const float opacity = __ldg(a.in.d_opacities + idx);
-
-                // Conservative extents of {alpha >= 1/255}: |dx| > ext_x  =>  power < -t  for every dy,
-                // because max_dy power = -dx^2 / (2 Sigma_xx) and Sigma_xx = cov.x (culling).
-                // Margins cover the fp32 rounding of the reference's power/exp/alpha evaluation.
-                float ext_x, ext_y, thr;
-                {
-                    const float t = logf(255.0f * opacity);
-                    const float reach = Rf + 16.0f;
-                    const float Sq = (fabsf(conic_x) + fabsf(conic_y) + fabsf(conic_z)) * reach * reach;
-                    const float kappa = fabsf(cov.x * cov.z * det_inv);
-                    const float tm = (t + 2e-3f + 1e-6f * Sq) * (1.0f + 2e-6f * kappa);
-                    // level of f = 0.5 (A dx^2 + C dy^2) + B dx dy above which no pixel contributes: tm, plus the rounding
-                    // of the exact test's own evaluation of f (same magnitude as the reference's, hence the same margin)
-                    thr = tm + 1e-3f + 1e-6f * Sq;
-                    if (!(thr == thr) || tm >= 1e30f) thr = __int_as_float(0x7f800000);
-                    if (tm < 0.0f || opacity <= 0.0f) {
-                        ext_x = __int_as_float(0xff800000); ext_y = ext_x;   // -inf: can never reach 1/255
-                    } else if (tm >= 0.0f && tm < 1e30f) {
-                        ext_x = sqrtf(2.0f * tm * cov.x) * 1.00001f + 1e-3f;
-                        ext_y = sqrtf(2.0f * tm * cov.z) * 1.00001f + 1e-3f;
-                        if (!(ext_x >= 0.0f)) ext_x = __int_as_float(0x7f800000);
-                        if (!(ext_y >= 0.0f)) ext_y = __int_as_float(0x7f800000);
-                    } else {
-                        ext_x = __int_as_float(0x7f800000); ext_y = ext_x;   // NaN/inf inputs: never cull
-                    }
-                    if (a.prm.debug & 2) { ext_x = __int_as_float(0x7f800000); ext_y = ext_x; thr = ext_x; }
-                }
-
-                SplatRec r;
-                r.q0 = make_float4(pix_x, pix_y, conic_x, conic_y);
-                r.q1 = make_float4(conic_z, opacity, cr, cg);
-                r.q2 = make_float4(cb, ext_x, ext_y, thr);
-                a.rec[idx] = r;
-                a.depth[idx] = depth;
-                a.clamped[idx] = clamp_bits;
-            }
-        }
-    }
-    if (valid) {
-        a.radii[idx] = radius;
-        a.rect[idx] = rect;
-    }
-
-    // ---- per-tile instance counts, warp-balanced ----
-    // The reference's duplicateWithKeys walks each splat's tile rectangle in a serial per-thread double loop
-    // (rasterizer_impl.cu:98-108) and so did round 1's counting here: one 12x12-tile splat kept its warp busy for 144
-    // dependent iterations (C5: preprocess 0.77 ms).  Same expansion as scatter_kernel (binning.cu): the warp scans its
-    // 32 rectangle sizes and walks the concatenated instance list 32 instances per step.
+// ---- per-tile instance counts for the 32 rectangles of a warp, warp-balanced ----
+// The reference's duplicateWithKeys walks each splat's tile rectangle in a serial per-thread double loop
+// (rasterizer_impl.cu:98-108) and so did round 1's counting here: one 12x12-tile splat kept its warp busy for 144
+// dependent iterations (C5: preprocess 0.77 ms).  Same expansion as scatter_kernel (binning.cu): the warp scans its
+// 32 rectangle sizes and walks the concatenated instance list 32 instances per step.
+__device__ __forceinline__ void count_tiles(const FwdArgs& a, uint2 rect, int idx, int lane) {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const uint32_t minx = rect.x & 0xffffu, miny = rect.x >> 16;
     const uint32_t w = (rect.y & 0xffffu) - minx;
     const uint32_t cnt = w * ((rect.y >> 16) - miny);          // 0 unless the Gaussian is rendered
     const unsigned vis = __ballot_sync(full, cnt != 0);
     if (vis == 0) return;
-    if (lane == 0) atomicAdd(a.counters + 3, (uint32_t)__popc(vis));      // FB200_ST_NUM_VISIBLE
+    // FB200_ST_NUM_VISIBLE, and the rendered Gaussians appended to the list the per-Gaussian backward runs over.  The
+    // atomic's result is consumed only after the tile walk below, which hides its round trip.
+    uint32_t at = 0;
+    if (lane == 0) at = atomicAdd(a.counters + 3, (uint32_t)__popc(vis));
     const uint32_t gxw = (uint32_t)a.tiles_x;
     if (__reduce_max_sync(full, cnt) <= 24u) {
         // small rectangles everywhere in the warp (the common frame): the plain per-lane walk is cheaper than the scan
@@ -385,39 +246,272 @@ preprocess_fwd_kernel(FwdArgs a) {
         if (cnt != 0)
             for (uint32_t ty = miny; ty < maxy; ++ty)
                 for (uint32_t tx = minx; tx < maxx; ++tx) atomicAdd(a.tile_count + ty * gxw + tx, 1u);
-        return;
-    }
-    uint32_t incl = cnt;
+    } else {
+        uint32_t incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(full, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const uint32_t excl = incl - cnt;
-    const uint32_t total = __shfl_sync(full, incl, 31);
-    const float rw = w ? __frcp_rn((float)w) : 0.f;
-    for (uint32_t base = 0; base < total; base += 32) {
-        const uint32_t item = base + lane;
-        int pos = 0;                      // owner = number of lanes whose inclusive count is <= item
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t excl = incl - cnt;
+        const uint32_t total = __shfl_sync(full, incl, 31);
+        const float rw = w ? __frcp_rn((float)w) : 0.f;
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t item = base + lane;
+            int pos = 0;                      // owner = number of lanes whose inclusive count is <= item
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            const uint32_t t = __shfl_sync(full, incl, pos + step - 1);
-            if (t <= item) pos += step;
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t t = __shfl_sync(full, incl, pos + step - 1);
+                if (t <= item) pos += step;
+            }
+            const int owner = min(pos, 31);
+            const uint32_t o_excl = __shfl_sync(full, excl, owner);
+            const uint32_t o_min = __shfl_sync(full, rect.x, owner);
+            const uint32_t o_w = __shfl_sync(full, w, owner);
+            const float o_rw = __shfl_sync(full, rw, owner);
+            if (item < total) {
+                const uint32_t k = item - o_excl;
+                // k / o_w through the reciprocal (both < 2^24), corrected by at most one either way
+                uint32_t q = __float2uint_rz(__fmul_rn((float)k, o_rw));
+                int rem = (int)k - (int)(q * o_w);
+                if (rem < 0) { --q; rem += (int)o_w; } else if (rem >= (int)o_w) { ++q; rem -= (int)o_w; }
+                const uint32_t ty = (o_min >> 16) + q, tx = (o_min & 0xffffu) + (uint32_t)rem;
+                atomicAdd(a.tile_count + ty * gxw + tx, 1u);
+            }
         }
-        const int owner = min(pos, 31);
-        const uint32_t o_excl = __shfl_sync(full, excl, owner);
-        const uint32_t o_min = __shfl_sync(full, rect.x, owner);
-        const uint32_t o_w = __shfl_sync(full, w, owner);
-        const float o_rw = __shfl_sync(full, rw, owner);
-        if (item < total) {
-            const uint32_t k = item - o_excl;
-            // k / o_w through the reciprocal (both < 2^24), corrected by at most one either way
-            uint32_t q = __float2uint_rz(__fmul_rn((float)k, o_rw));
-            int rem = (int)k - (int)(q * o_w);
-            if (rem < 0) { --q; rem += (int)o_w; } else if (rem >= (int)o_w) { ++q; rem -= (int)o_w; }
-            const uint32_t ty = (o_min >> 16) + q, tx = (o_min & 0xffffu) + (uint32_t)rem;
-            atomicAdd(a.tile_count + ty * gxw + tx, 1u);
+    }
+    at = __shfl_sync(full, at, 0);
+    if (cnt != 0) a.vis_list[at + __popc(vis & ((1u << lane) - 1u))] = (uint32_t)idx;
+}
+
+// Everything after the cull for ONE surviving Gaussian: projection, covariance, conic, radius, tile rectangle, colour,
+// culling extents, the packed record.  kFrost: attributes come straight from Frosting's parameters (frosting_attr.cuh).
+template <bool kFrost>
+__device__ __forceinline__ void project_gaussian(const FwdArgs& a, const CamConst& cam, int idx, float px, float py,
+                                                 float pz, int& radius, uint2& rect) {
+    const float* __restrict__ v = cam.view;
+    const float* __restrict__ m = cam.proj;
+    const fb200_frosting_params& fr = a.fr;
+    const float depth = affine_row(v, 2, px, py, pz);
+    const float hx = affine_row(m, 0, px, py, pz);
+    const float hy = affine_row(m, 1, px, py, pz);
+    const float hw = affine_row(m, 3, px, py, pz);
+    const float p_w = __frcp_rn(fadd(hw, 0.0000001f));
+    const float projx = fmul(hx, p_w);
+    const float projy = fmul(hy, p_w);
+
+    Cov3 S;
+    if (kFrost) {
+        const float* ls = fr.d_log_scales + 3 * (size_t)idx;
+        float nrm;
+        const float4 q = frost_normalize(__ldg(reinterpret_cast<const float4*>(fr.d_quats) + idx), nrm);
+        S = cov3d_from_scale_rot(expf(__ldg(ls)), expf(__ldg(ls + 1)), expf(__ldg(ls + 2)), a.prm.scale_modifier,
+                                 q.x, q.y, q.z, q.w);
+    } else if (a.in.d_cov3D_precomp != nullptr) {
+        const float* c = a.in.d_cov3D_precomp + 6 * (size_t)idx;
+        S.c0 = __ldg(c + 0); S.c1 = __ldg(c + 1); S.c2 = __ldg(c + 2);
+        S.c3 = __ldg(c + 3); S.c4 = __ldg(c + 4); S.c5 = __ldg(c + 5);
+    } else {
+        const float* sc = a.in.d_scales + 3 * (size_t)idx;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.in.d_rotations) + idx);
+        S = cov3d_from_scale_rot(__ldg(sc), __ldg(sc + 1), __ldg(sc + 2), a.prm.scale_modifier, q.x, q.y, q.z, q.w);
+    }
+
+    const float3 cov = cov2d(px, py, pz, a.focal_x, a.focal_y, a.prm.tanfovx, a.prm.tanfovy, S, v);
+    const float det = ffma(cov.x, cov.z, -fmul(cov.y, cov.y));
+    if (det == 0.0f) return;
+    const float det_inv = __frcp_rn(det);
+    const float conic_x = fmul(cov.z, det_inv);
+    const float conic_y = fmul(cov.y, -det_inv);
+    const float conic_z = fmul(cov.x, det_inv);
+    const float mid = fmul(fadd(cov.x, cov.z), 0.5f);
+    const float sq = __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f));
+    const float lambda1 = fadd(mid, sq);
+    const float lambda2 = fadd(mid, -sq);
+    const float rad_f = fmul(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.0f);
+    const int my_radius = __float2int_ru(rad_f);
+    const float Rf = (float)my_radius;
+    const float pix_x = ndc2pix(projx, a.prm.image_width);
+    const float pix_y = ndc2pix(projy, a.prm.image_height);
+    // getRect, auxiliary.h:46-56
+    const uint32_t gx = (uint32_t)a.tiles_x, gy = (uint32_t)a.tiles_y;
+    const uint32_t minx = rect_coord(fadd(pix_x, -Rf), gx);
+    const uint32_t miny = rect_coord(fadd(pix_y, -Rf), gy);
+    const uint32_t maxx = rect_coord(fadd(fadd(fadd(pix_x, Rf), 16.0f), -1.0f), gx);
+    const uint32_t maxy = rect_coord(fadd(fadd(fadd(pix_y, Rf), 16.0f), -1.0f), gy);
+    const uint32_t touched = (maxx - minx) * (maxy - miny);
+    if (touched == 0) return;
+    radius = my_radius;
+    rect = make_uint2(minx | (miny << 16), maxx | (maxy << 16));
+
+    float cr, cg, cb;
+    uint8_t clamp_bits = 0;
+    if (kFrost || a.in.d_colors_precomp == nullptr) {
+        // direction = (p - campos) / |p - campos|   (glm::length = sqrt(dot))
+        const float dx = fadd(-cam.campos[0], px);
+        const float dy = fadd(-cam.campos[1], py);
+        const float dz = fadd(-cam.campos[2], pz);
+        const float len = __fsqrt_rn(dot3x(dx, dx, dy, dy, dz, dz));
+        const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+        float c[48];
+        if (kFrost) {
+            load_sh_split(a.prm.sh_degree, fr.d_sh_dc + 3 * (size_t)idx, fr.d_sh_rest + (size_t)idx * fr.sh_rest * 3, c);
+        } else {
+            const float* sh = a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3;
+            if ((a.prm.sh_coeffs & 3) == 0) load_sh<true>(a.prm.sh_degree, sh, c);
+            else load_sh<false>(a.prm.sh_degree, sh, c);
         }
+        float r0, r1, r2;
+        eval_sh(a.prm.sh_degree, c, x, y, z, r0, r1, r2);
+        // result += 0.5; clamped = result < 0; result = max(result, 0)
+        const float s0 = fadd(r0, 0.5f), s1 = fadd(r1, 0.5f), s2 = fadd(r2, 0.5f);
+        clamp_bits = (s0 < 0.f ? 1 : 0) | (s1 < 0.f ? 2 : 0) | (s2 < 0.f ? 4 : 0);
+        cr = (s0 < 0.f) ? 0.f : s0;
+        cg = (s1 < 0.f) ? 0.f : s1;
+        cb = (s2 < 0.f) ? 0.f : s2;
+    } else {
+        const float* c = a.in.d_colors_precomp + 3 * (size_t)idx;
+        cr = __ldg(c); cg = __ldg(c + 1); cb = __ldg(c + 2);
+    }
+    const float opacity = kFrost ? frost_sigmoid(__ldg(fr.d_opacity_logits + idx)) : __ldg(a.in.d_opacities + idx);
+
+    // Conservative extents of {alpha >= 1/255}: |dx| > ext_x  =>  power < -t  for every dy,
+    // because max_dy power = -dx^2 / (2 Sigma_xx) and Sigma_xx = cov.x (culling).
+    // Margins cover the fp32 rounding of the reference's power/exp/alpha evaluation.
+    float ext_x, ext_y, thr;
+    {
+        const float t = logf(255.0f * opacity);
+        const float reach = Rf + 16.0f;
+        const float Sq = (fabsf(conic_x) + fabsf(conic_y) + fabsf(conic_z)) * reach * reach;
+        const float kappa = fabsf(cov.x * cov.z * det_inv);
+        const float tm = (t + 2e-3f + 1e-6f * Sq) * (1.0f + 2e-6f * kappa);
+        // level of f = 0.5 (A dx^2 + C dy^2) + B dx dy above which no pixel contributes: tm, plus the rounding
+        // of the exact test's own evaluation of f (same magnitude as the reference's, hence the same margin)
+        thr = tm + 1e-3f + 1e-6f * Sq;
+        if (!(thr == thr) || tm >= 1e30f) thr = __int_as_float(0x7f800000);
+        if (tm < 0.0f || opacity <= 0.0f) {
+            ext_x = __int_as_float(0xff800000); ext_y = ext_x;   // -inf: can never reach 1/255
+        } else if (tm >= 0.0f && tm < 1e30f) {
+            ext_x = sqrtf(2.0f * tm * cov.x) * 1.00001f + 1e-3f;
+            ext_y = sqrtf(2.0f * tm * cov.z) * 1.00001f + 1e-3f;
+            if (!(ext_x >= 0.0f)) ext_x = __int_as_float(0x7f800000);
+            if (!(ext_y >= 0.0f)) ext_y = __int_as_float(0x7f800000);
+        } else {
+            ext_x = __int_as_float(0x7f800000); ext_y = ext_x;   // NaN/inf inputs: never cull
+        }
+        if (a.prm.debug & 2) { ext_x = __int_as_float(0x7f800000); ext_y = ext_x; thr = ext_x; }
+    }
+
+    SplatRec r;
+    r.q0 = make_float4(pix_x, pix_y, conic_x, conic_y);
+    r.q1 = make_float4(conic_z, opacity, cr, cg);
+    r.q2 = make_float4(cb, ext_x, ext_y, thr);
+    a.rec[idx] = r;
+    a.depth[idx] = depth;
+    a.clamped[idx] = clamp_bits;
+}
+
+// A CTA owns kPreSpan consecutive Gaussians.  Phase A: every thread culls kPreRounds of them (occlusion lookup +
+// near plane: two short load chains) and the survivors -- ~10 % of a Frosting layer under occlusion culling -- are
+// compacted into shared memory.  Phase B: the heavy part runs over the compacted list with full warps.  Round 1/2a
+// ran the heavy part in place: 11.75 of 32 lanes active per instruction (profiles/r02_c3_v10_summary.json).
+template <bool kFrost>
+__global__ void __launch_bounds__(kPreThreads, FB200_PRE_CTAS)
+preprocess_fwd_kernel(FwdArgs a) {
+    __shared__ CamConst cam;
+    __shared__ float4 items[kPreSpan];       // {x, y, z, index bits}
+    __shared__ int n_items;
+    if (threadIdx.x < 16) {
+        cam.view[threadIdx.x] = a.in.d_viewmatrix[threadIdx.x];
+        cam.proj[threadIdx.x] = a.in.d_projmatrix[threadIdx.x];
+    }
+    if (threadIdx.x < 3) cam.campos[threadIdx.x] = a.in.d_campos[threadIdx.x];
+    if (threadIdx.x == 0) n_items = 0;
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    const int P = a.prm.P;
+    const int lane = threadIdx.x & 31;
+    const int base = blockIdx.x * kPreSpan;
+    const float* __restrict__ v = cam.view;
+
+    // ---- phase A: cull ----
+    // the occlusion inputs first: the cell -> visible-face gather is a dependent chain of its own, started before the
+    // position loads so that the two chains overlap (a culled Gaussian then costs two memory round trips, not three)
+    long long cell[kPreRounds];
+    uint8_t vis_in[kPreRounds];
+#pragma unroll
+    for (int r = 0; r < kPreRounds; ++r) {
+        const int tid = base + r * kPreThreads + threadIdx.x;
+        const int idx = tid < P ? tid : P - 1;
+        const bool by_face = a.in.d_face_visible != nullptr && (long long)idx < a.in.n_cell_points;
+        cell[r] = by_face ? __ldg(a.in.d_point_cells + idx) : -1;
+        vis_in[r] = a.in.d_visibility != nullptr ? __ldg(a.in.d_visibility + idx) : (uint8_t)1;
+    }
+#pragma unroll
+    for (int r = 0; r < kPreRounds; ++r) {
+        const int tid = base + r * kPreThreads + threadIdx.x;
+        if (base + r * kPreThreads >= P) break;               // CTA-uniform
+        const bool valid = tid < P;
+        const int idx = valid ? tid : P - 1;
+        // occlusion culling: a per-Gaussian mask tensor, or -- without one -- render_mask = face_visible[_point_cell_indices]
+        // for the mesh-bound Gaussians, True for the trailing background ones (frosting_model.py:1564-1576), looked up in place
+        const uint8_t face_in = cell[r] >= 0 ? __ldg(a.in.d_face_visible + cell[r]) : (uint8_t)1;
+        const bool shown = vis_in[r] != 0 && face_in != 0;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (kFrost) {
+            if (shown) { float w[6]; int vid[3]; frost_point(a.fr, (size_t)idx, w, vid, px, py, pz); }
+        } else {
+            px = __ldg(a.in.d_means3D + 3 * (size_t)idx + 0);
+            py = __ldg(a.in.d_means3D + 3 * (size_t)idx + 1);
+            pz = __ldg(a.in.d_means3D + 3 * (size_t)idx + 2);
+        }
+        // in_frustum: keep iff !(p_view.z <= 0.2f)
+        const float depth = affine_row(v, 2, px, py, pz);
+        bool keep = valid && !(depth <= 0.2f);
+        if (valid && !keep && a.prm.prefiltered && (!kFrost || shown)) {
+            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+            __trap();
+        }
+        if (!shown) keep = false;
+        if (keep) {
+            // the SH row (192 B at degree 3) is consumed last, after a chain of dependent loads; start it moving now
+            const char* row = kFrost ? reinterpret_cast<const char*>(a.fr.d_sh_rest + (size_t)idx * a.fr.sh_rest * 3)
+                                     : reinterpret_cast<const char*>(a.in.d_shs + (size_t)idx * a.prm.sh_coeffs * 3);
+            if (kFrost || a.in.d_shs != nullptr) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+                if (a.prm.sh_coeffs * 12 > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));
+            }
+        } else if (valid) {
+            a.radii[idx] = 0;
+            a.rect[idx] = make_uint2(0u, 0u);
+        }
+        const unsigned kept = __ballot_sync(full, keep);
+        if (kept != 0) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&n_items, __popc(kept));
+            slot = __shfl_sync(full, slot, 0) + __popc(kept & ((1u << lane) - 1u));
+            if (keep) items[slot] = make_float4(px, py, pz, __int_as_float(idx));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: project the survivors, full warps ----
+    const int n = n_items;
+    static_assert(kPreRounds == 1, "phase B below handles one round (n <= kPreThreads)");
+    const int jb = threadIdx.x & ~31;
+    if (jb < n) {                                                       // warp-uniform
+        const int j = jb + lane;
+        int radius = 0, idx = 0;
+        uint2 rect = make_uint2(0u, 0u);
+        if (j < n) {
+            const float4 it = items[j];
+            idx = __float_as_int(it.w);
+            project_gaussian<kFrost>(a, cam, idx, it.x, it.y, it.z, radius, rect);
+            a.radii[idx] = radius;
+            a.rect[idx] = rect;
+        }
+        count_tiles(a, rect, idx, lane);
     }
 }
 
@@ -441,8 +535,9 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(a.tile_count, 0, span, s);
     if (e != cudaSuccess) return e;
     if (a.prm.P > 0) {
-        const int blocks = (a.prm.P + 255) / 256;
-        preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(a);
+        const int blocks = (a.prm.P + kPreSpan - 1) / kPreSpan;
+        if (a.frosting) preprocess_fwd_kernel<true><<<blocks, kPreThreads, 0, s>>>(a);
+        else preprocess_fwd_kernel<false><<<blocks, kPreThreads, 0, s>>>(a);
         count_launch();
     }
     return cudaGetLastError();

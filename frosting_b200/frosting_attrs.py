@@ -27,7 +27,9 @@ class _FrostingAttributes(torch.autograd.Function):
         if not bary_logits.is_cuda:
             raise RuntimeError("frosting_b200 runs on CUDA tensors only (no CPU fallback)")
         dev = bary_logits.device
-        t = [x.contiguous() for x in (bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer)]
+        # contiguous, and copied if a view starts at an address the kernels' 64/128-bit row accesses cannot use
+        t = [x.contiguous() if x.contiguous().data_ptr() % 16 == 0 else x.contiguous().clone()
+             for x in (bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer)]
         bary_logits, opacity_logits, log_scales, quats, sh_dc, sh_rest, inner, outer = t
         cells = cells.to(device=dev, dtype=torch.int64).contiguous()
         faces = faces.to(device=dev, dtype=torch.int32).contiguous()

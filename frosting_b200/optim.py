@@ -109,10 +109,22 @@ class GradSink(dict):
     Producers OVERWRITE their views (one write per element, no read-modify-write), so a second fused backward into
     the sink before the step would silently drop the first: `sink_once` raises instead."""
 
+    accepts_row_radii = False     # set per instance by FlatSlabs(rows=...)
+
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
         self.written = set()
         self.sunk = set()
+        # sparse-row producers (frosting_render): `row_radii` [rows] int32 of the frame that wrote the views named in
+        # `sparse_names`; rows with radii <= 0 are zero rows that were NOT written and must not be read
+        self.row_radii = None
+        self.sparse_names = set()
+
+    def rows_from(self, radii, names):
+        if not self.accepts_row_radii:
+            raise RuntimeError("this gradient sink has no row structure: zero-fill instead")
+        self.row_radii = radii
+        self.sparse_names |= set(names)
 
     def __getitem__(self, name):
         self.written.add(name)
@@ -130,12 +142,17 @@ class GradSink(dict):
     def clear(self):   # not dict.clear: the views stay
         self.written = set()
         self.sunk = set()
+        self.row_radii = None
+        self.sparse_names = set()
 
 
 class FlatSlabs:
     """Parameter and gradient slabs + named views.  `tensors`: ordered dict name -> initial CUDA tensor."""
 
-    def __init__(self, tensors, world=1, rank=0, peer=False, group=None):
+    def __init__(self, tensors, world=1, rank=0, peer=False, group=None, rows=None):
+        """`rows`: when given, tensors whose first dimension equals it are row-structured (one row per Gaussian) and the
+        gradient slab carries a [rows] int32 radii region behind the gradients -- peer-visible like the slab itself --
+        through which a sparse-row producer tells every rank's step which of ITS rows exist (fb200_adam_args.peer_row_radii)."""
         names = list(tensors)
         first = tensors[names[0]]
         if not first.is_cuda:
@@ -143,6 +160,10 @@ class FlatSlabs:
         self.device, self.names, self.world, self.rank, self.group = first.device, names, world, rank, group
         self.shapes = {n: tuple(tensors[n].shape) for n in names}
         self.starts, self.total = slab_layout([tensors[n].numel() for n in names], world)
+        self.rows = int(rows) if rows else 0
+        self.row_width = [tensors[n].numel() // self.rows if self.rows and tensors[n].dim() >= 1 and
+                          tensors[n].shape[0] == self.rows else 0 for n in names]
+        self.alloc = self.total + (self.rows + 3) // 4 * 4       # elements allocated per slab: Adam's range + the radii region
         self._owned, self._opened = [], []
         self.mc_params = self.mc_grads = 0      # NVSwitch multicast mappings of the two slabs (0: none)
         self.transport = "local"
@@ -154,18 +175,22 @@ class FlatSlabs:
                 ptrs = []
                 for _ in range(2):
                     p = C.c_void_p()
-                    _lib.check(L.fb200_peer_alloc(self.total * 4, C.byref(p)))
+                    _lib.check(L.fb200_peer_alloc(self.alloc * 4, C.byref(p)))
                     self._owned.append(p.value)
                     ptrs.append(p.value)
-                self.param_slab = _view(ptrs[0], self.total, self.device)
-                self.grad_slab = _view(ptrs[1], self.total, self.device)
+                self.param_slab = _view(ptrs[0], self.alloc, self.device)
+                self.grad_slab = _view(ptrs[1], self.alloc, self.device)
                 self.peer_params, self.peer_grads = self._exchange(L, ptrs)
                 self.transport = "cudaIpc peer pointers"
         else:
-            self.param_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
-            self.grad_slab = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self.param_slab = torch.zeros(self.alloc, dtype=torch.float32, device=self.device)
+            self.grad_slab = torch.zeros(self.alloc, dtype=torch.float32, device=self.device)
             self.peer_params, self.peer_grads = [self.param_slab.data_ptr()], [self.grad_slab.data_ptr()]
         self.params, self.grads = {}, GradSink()
+        self.row_radii = None
+        if self.rows:
+            self.grads.accepts_row_radii = True
+            self.row_radii = self.grad_slab[self.total:self.total + self.rows].view(torch.int32)
         for n, s in zip(names, self.starts):
             k = tensors[n].numel()
             self.param_slab[s:s + k].copy_(tensors[n].detach().reshape(-1).to(torch.float32))
@@ -190,7 +215,7 @@ class FlatSlabs:
                 group = self.group if self.group is not None else dist.group.WORLD
                 with torch.cuda.device(self.device):
                     for _ in range(2):
-                        t = symm.empty(self.total, dtype=torch.float32, device=self.device)
+                        t = symm.empty(self.alloc, dtype=torch.float32, device=self.device)
                         t.zero_()
                         slabs.append(t)
                     torch.cuda.synchronize(self.device)
@@ -268,7 +293,7 @@ class FrostingAdam:
     in its backward; `opt.collect_grads()` copies autograd's `.grad` there for any other producer -- `step()` does it
     itself when nothing was written).  `state_dict()` / `load_state_dict()` speak torch.optim.Adam's format."""
 
-    def __init__(self, tensors, lrs, betas=(0.9, 0.999), eps=1e-15, group=None, average=True):
+    def __init__(self, tensors, lrs, betas=(0.9, 0.999), eps=1e-15, group=None, average=True, rows=None):
         if len(tensors) > _lib.ADAM_MAX_GROUPS:
             raise ValueError(f"at most {_lib.ADAM_MAX_GROUPS} parameter groups")
         self.group = group
@@ -277,7 +302,7 @@ class FrostingAdam:
         self.rank = dist.get_rank(group) if distributed else 0
         if self.world > _lib.MAX_PEERS:
             raise ValueError(f"at most {_lib.MAX_PEERS} ranks (one NVSwitch box)")
-        self.slabs = FlatSlabs(tensors, self.world, self.rank, peer=self.world > 1, group=group)
+        self.slabs = FlatSlabs(tensors, self.world, self.rank, peer=self.world > 1, group=group, rows=rows)
         self.params, self.grads = self.slabs.params, self.slabs.grads
         self.param_groups = [{"name": n, "lr": float(lrs[n]), "params": [self.params[n]]} for n in self.slabs.names]
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
@@ -301,7 +326,8 @@ class FrostingAdam:
         order = ("bary_logits", "sh_dc", "sh_rest", "opacity_logits", "log_scales", "quats")
         lr = {"bary_logits": opt.position_bary_coords_lr_init, "sh_dc": opt.feature_lr, "sh_rest": opt.feature_lr / 20.0,
               "opacity_logits": opt.opacity_lr, "log_scales": opt.scaling_lr, "quats": opt.rotation_lr}
-        self = cls({n: params[n] for n in order}, lr, eps=1e-15, group=group)
+        # one row per Gaussian in every tensor: `frosting_render` writes the rendered rows only and hands `radii` over
+        self = cls({n: params[n] for n in order}, lr, eps=1e-15, group=group, rows=params["bary_logits"].shape[0])
         for g in self.param_groups:
             g["name"] = cls.GROUP_OF[g["name"]]
         self.num_iterations = opt.iterations
@@ -372,6 +398,13 @@ class FrostingAdam:
         a.grad_scale = self.grad_scale
         a.mc_grads = self.slabs.mc_grads or None
         a.mc_params = self.slabs.mc_params or None
+        if self.grads.row_radii is not None:
+            # sparse gradient rows: every rank's radii sit behind its gradient slab, so the peer mappings cover them
+            for r in range(self.world):
+                a.peer_row_radii[r] = self.slabs.peer_grads[r] + 4 * self.slabs.total
+            for k, n in enumerate(self.slabs.names):
+                a.row_width[k] = self.slabs.row_width[k] if n in self.grads.sparse_names else 0
+            a.row_count = self.slabs.rows
         return a
 
     def step(self, loss=None):
@@ -381,6 +414,8 @@ class FrostingAdam:
         dev = self.slabs.device
         if not self.grads.written:
             self.collect_grads()            # plain autograd use: .grad populated, nobody copied it
+        if self.grads.row_radii is not None:
+            self.slabs.row_radii.copy_(self.grads.row_radii)      # 4 B per Gaussian; ordered before rendezvous 1
         if self.world > 1:
             # rendezvous 1: every rank's backward (its gradient slab) is complete before any shard is read
             dist.all_reduce(loss if loss is not None else self._flag, group=self.group)

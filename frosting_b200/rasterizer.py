@@ -257,6 +257,25 @@ def _prepare(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_p
     return device, P, W, H, prm, inp, tensors, extra_features, extra_bg
 
 
+def _prepare_frosting(frosting, rs):
+    """Frosting mode (fb200_inputs.frosting): the rasterizer reads the parameter block `fp` itself; no attribute tensors."""
+    fp, keep, device = frosting
+    P, M = int(fp.P), int(fp.sh_rest) + 1
+    H, W = int(rs.image_height), int(rs.image_width)
+    bg = _f32c(rs.bg, device, "bg")
+    view = _f32c(rs.viewmatrix, device, "viewmatrix")
+    proj = _f32c(rs.projmatrix, device, "projmatrix")
+    campos = _f32c(rs.campos, device, "campos")
+    prm = Params(P=P, sh_degree=int(rs.sh_degree), sh_coeffs=M, image_width=W, image_height=H,
+                 tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
+                 scale_modifier=float(rs.scale_modifier), prefiltered=int(bool(rs.prefiltered)),
+                 debug=int(bool(rs.debug)) | (2 if NO_CULL else 0) | (4 if BWD_PAIR_KERNEL else 0) | (16 if BWD_OCC24 else 0),
+                 extra=None)
+    inp = Inputs(d_background=_ptr(bg), d_viewmatrix=_ptr(view), d_projmatrix=_ptr(proj), d_campos=_ptr(campos),
+                 n_cell_points=0, frosting=C.addressof(fp))
+    return device, P, W, H, prm, inp, (fp, keep, bg, view, proj, campos), None, None
+
+
 def _attach_stream(L, ws, capacity, device):
     """TMA A/B only: the packed record stream workspace (48 B per tile instance)."""
     if not FWD_TMA:
@@ -268,7 +287,7 @@ def _attach_stream(L, ws, capacity, device):
 
 def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                     rs: GaussianRasterizationSettings, visibility, extra_features=None, extra_bg=None,
-                    want_backward=False, exact=False, geometry_only=False, face_visibility=None):
+                    want_backward=False, exact=False, geometry_only=False, face_visibility=None, frosting=None):
     """One forward through the C ABI.
 
     Default: ONE-PHASE, no host wait.  `fb200_forward` is launched with a binning capacity speculated from earlier frames
@@ -280,9 +299,12 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
     blocks at the same point, rasterizer_impl.cu:280-281), raster phase with an exactly sized buffer.
     """
     L = _lib.lib()
-    device, P, W, H, prm, inp, tensors, extra_features, extra_bg = _prepare(
-        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, visibility, extra_features,
-        extra_bg, face_visibility)
+    if frosting is not None:
+        device, P, W, H, prm, inp, tensors, extra_features, extra_bg = _prepare_frosting(frosting, rs)
+    else:
+        device, P, W, H, prm, inp, tensors, extra_features, extra_bg = _prepare(
+            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, visibility, extra_features,
+            extra_bg, face_visibility)
     host = _host_state(device)
     host.poll()
     extra = None
@@ -357,7 +379,8 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
     return out_color, radii, call, out_extra
 
 
-def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None, sparse_rows=False):
+def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None, sparse_rows=False,
+                     frosting_grads=None):
     L = _lib.lib()
     call.check()       # a speculatively launched forward that overflowed has no state to differentiate: raise
     prm = call.prm
@@ -369,6 +392,14 @@ def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None, 
         if g.dtype != torch.float32:
             g = g.float()
         g = g.contiguous()
+        if frosting_grads is not None:
+            # frosting mode: the per-Gaussian backward writes the parameter gradients (rendered rows only)
+            grads = Grads(sparse_rows=1, frosting=C.addressof(frosting_grads))
+            _lib.check(L.fb200_backward(C.byref(prm), C.byref(call.inp), C.byref(call.ws),
+                                        C.c_void_p(radii.data_ptr()) if P > 0 else None,
+                                        C.c_void_p(g.data_ptr()), C.byref(grads), C.c_void_p(stream.cuda_stream)))
+            call.ws.acc_zeroed_by_forward = 0
+            return None
         # one allocation carved into the gradient tensors the caller can use (each offset a multiple of 4 floats);
         # dL/dcolors on the SH path, dL/dcov3D on the scale/rotation path and dL/dscales, dL/drotations on the
         # precomputed-covariance path are never returned (`backward` below) and are not materialised

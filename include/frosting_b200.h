@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 3
+#define FB200_ABI_VERSION 4
 
 #define FB200_OK 0
 #define FB200_EINVAL (-1)   /* bad argument (shape / null pointer / unsupported channel count) */
@@ -76,6 +76,35 @@ typedef struct fb200_params {
     const fb200_extra* extra; /* NULL: colour only (the reference's surface) */
 } fb200_params;
 
+/* Frosting's per-frame attribute construction, fused (frosting_scene/frosting_model.py:713-799): turns the
+ * model's learnable parameters into the rasterizer inputs in one kernel (and one backward kernel) instead
+ * of the softmax / gather / mul / sum / sigmoid / exp / normalize / cat chain of torch ops. */
+typedef struct fb200_frosting_params {
+    int32_t P;                       /* mesh-bound Gaussians */
+    int32_t n_verts, n_faces;        /* shell base mesh */
+    int32_t sh_rest;                 /* M - 1: coefficients in _sh_coordinates_rest */
+    const float* d_bary_logits;      /* [P,6]  _bary_coords (softmax logits, :713-716) */
+    const int64_t* d_cells;          /* [P]    _point_cell_indices */
+    const int32_t* d_faces;          /* [F,3]  _shell_base_faces */
+    const float* d_inner_verts;      /* [V,3]  inner_verts property (:679-710) */
+    const float* d_outer_verts;      /* [V,3]  outer_verts */
+    const float* d_opacity_logits;   /* [P]    _opacities */
+    const float* d_log_scales;       /* [P,3]  _scales (scale_activation = exp, :32) */
+    const float* d_quats;            /* [P,4]  _quaternions (raw) */
+    const float* d_sh_dc;            /* [P,1,3] */
+    const float* d_sh_rest;          /* [P,M-1,3] */
+    const uint8_t* d_mask;           /* optional [P]: 0 = occluded, outputs for it are left untouched */
+    const uint8_t* d_face_visible;   /* optional [F]: the same culling as face_visible[d_cells[i]] (no mask tensor) */
+    const int32_t* d_radii;          /* optional [P], backward only: a Gaussian with radii <= 0 was not rendered, its
+                                        upstream gradient rows are zero by definition and are NOT read (they may be
+                                        unwritten: fb200_grads.sparse_rows) */
+} fb200_frosting_params;
+
+typedef struct fb200_frosting_grads {      /* all fully written; inner/outer vertex gradients are accumulated */
+    float* d_bary_logits; float* d_inner_verts; float* d_outer_verts; float* d_opacity_logits;
+    float* d_log_scales; float* d_quats; float* d_sh_dc; float* d_sh_rest;
+} fb200_frosting_grads;
+
 /* Device inputs of the forward pass.  Exactly one of (d_shs | d_colors_precomp) and exactly one of
  * (d_scales + d_rotations | d_cov3D_precomp) must be non-null, as GaussianRasterizer.forward
  * requires (__init__.py:191-195). */
@@ -100,6 +129,15 @@ typedef struct fb200_inputs {
     const int64_t* d_point_cells;  /* [n_cell_points] or NULL */
     const uint8_t* d_face_visible; /* [F] (0 = occluded) or NULL */
     int64_t n_cell_points;         /* mesh-bound Gaussians (<= P) */
+    /* FROSTING MODE (row f1 proper): the rasterizer reads Frosting's learnable parameters directly.  When non-NULL,
+     * d_means3D, d_shs, d_colors_precomp, d_opacities, d_scales, d_rotations, d_cov3D_precomp, d_visibility,
+     * d_point_cells and d_face_visible above must all be NULL: preprocess builds position (softmax barycentrics over the
+     * prism cell), opacity (sigmoid), scales (exp), rotation (normalize) and reads the SH rows from dc | rest IN PLACE --
+     * no attribute tensor, in particular no [P,M,3] SH copy, is ever materialised -- and culls with
+     * frosting->d_mask / frosting->d_face_visible[d_cells[i]].  prm->P == frosting->P, prm->sh_coeffs == sh_rest + 1.
+     * fb200_backward then needs fb200_grads.frosting and writes the PARAMETER gradients (same chain rule as
+     * fb200_frosting_attributes_backward, inside the per-Gaussian backward kernel). */
+    const fb200_frosting_params* frosting;
 } fb200_inputs;
 
 /* Alignment: rows that the kernels read or write with 128-bit accesses must start on 16-byte boundaries -- d_rotations,
@@ -172,9 +210,13 @@ typedef struct fb200_grads {
     float* d_dL_dscales;      /* [P,3]; these two may be NULL when d_cov3D_precomp is given */
     float* d_dL_drotations;   /* [P,4] */
     int32_t sparse_rows;      /* 0: every row is written (zeros for Gaussians with radii == 0) -- the reference's dense
-                                 contract.  1 (row f1): runs of 32 Gaussians that were all not rendered are SKIPPED: their
-                                 rows stay unwritten and must not be read -- for a consumer that has d_radii and treats
-                                 radii <= 0 as a zero row (fb200_frosting_attributes_backward with d_radii) */
+                                 contract.  1 (row f1): rows of Gaussians that were not rendered (radii <= 0) are
+                                 SKIPPED: they stay unwritten and must not be read -- for a consumer that has d_radii and
+                                 treats radii <= 0 as a zero row (fb200_frosting_attributes_backward with d_radii,
+                                 fb200_adam_args.d_row_radii) */
+    const fb200_frosting_grads* frosting; /* frosting mode (fb200_inputs.frosting): the parameter-gradient outputs; the
+                                 eight pointers above may then be NULL (d_dL_dmeans2D is still written when given) and
+                                 the contract is ALWAYS sparse: only rows with radii > 0 are written */
 } fb200_grads;
 
 int fb200_backward(const fb200_params* prm, const fb200_inputs* in, const fb200_workspace* ws,
@@ -207,35 +249,7 @@ int fb200_gaussian_mask_from_faces(int32_t n_points, const int64_t* d_point_cell
                                    int32_t F, const uint8_t* d_face_visible, int32_t n_background,
                                    uint8_t* d_mask, void* stream);
 
-/* Frosting's per-frame attribute construction, fused (frosting_scene/frosting_model.py:713-799): turns the
- * model's learnable parameters into the rasterizer inputs in one kernel (and one backward kernel) instead
- * of the softmax / gather / mul / sum / sigmoid / exp / normalize / cat chain of torch ops. */
-typedef struct fb200_frosting_params {
-    int32_t P;                       /* mesh-bound Gaussians */
-    int32_t n_verts, n_faces;        /* shell base mesh */
-    int32_t sh_rest;                 /* M - 1: coefficients in _sh_coordinates_rest */
-    const float* d_bary_logits;      /* [P,6]  _bary_coords (softmax logits, :713-716) */
-    const int64_t* d_cells;          /* [P]    _point_cell_indices */
-    const int32_t* d_faces;          /* [F,3]  _shell_base_faces */
-    const float* d_inner_verts;      /* [V,3]  inner_verts property (:679-710) */
-    const float* d_outer_verts;      /* [V,3]  outer_verts */
-    const float* d_opacity_logits;   /* [P]    _opacities */
-    const float* d_log_scales;       /* [P,3]  _scales (scale_activation = exp, :32) */
-    const float* d_quats;            /* [P,4]  _quaternions (raw) */
-    const float* d_sh_dc;            /* [P,1,3] */
-    const float* d_sh_rest;          /* [P,M-1,3] */
-    const uint8_t* d_mask;           /* optional [P]: 0 = occluded, outputs for it are left untouched */
-    const uint8_t* d_face_visible;   /* optional [F]: the same culling as face_visible[d_cells[i]] (no mask tensor) */
-    const int32_t* d_radii;          /* optional [P], backward only: a Gaussian with radii <= 0 was not rendered, its
-                                        upstream gradient rows are zero by definition and are NOT read (they may be
-                                        unwritten: fb200_grads.sparse_rows) */
-} fb200_frosting_params;
-
-typedef struct fb200_frosting_grads {      /* all fully written; inner/outer vertex gradients are accumulated */
-    float* d_bary_logits; float* d_inner_verts; float* d_outer_verts; float* d_opacity_logits;
-    float* d_log_scales; float* d_quats; float* d_sh_dc; float* d_sh_rest;
-} fb200_frosting_grads;
-
+/* Frosting's attribute construction as stand-alone kernels (structs: above, before fb200_inputs). */
 int fb200_frosting_attributes(const fb200_frosting_params* fp, float* d_means3D /*[P,3]*/, float* d_opacities /*[P,1]*/,
                               float* d_scales /*[P,3]*/, float* d_rotations /*[P,4]*/, float* d_shs /*[P,M,3]*/,
                               void* stream);
@@ -287,6 +301,16 @@ typedef struct fb200_adam_args {
      * new parameters are broadcast by the switch (multimem.st): 1/world of the wire bytes of the peer-pointer path. */
     const float* mc_grads;
     float* mc_params;
+    /* Sparse gradient rows (the producers' contract: fb200_grads.sparse_rows, frosting mode).  Optional, for all ranks or
+     * none: peer_row_radii[r] is rank r's [row_count] radii of the frame that produced its gradient slab, mapped on THIS
+     * device like peer_grads[r].  In a group with row_width[g] > 0, element j belongs to row j / row_width[g]; a row whose
+     * radii is <= 0 on rank r is a ZERO row of r's gradient and its slab elements are NOT READ (they may be unwritten) --
+     * ~90 % of a frosting layer per camera, so the step reads a tenth of the gradient bytes, locally and over NVLink.
+     * The in-switch sum cannot skip rows: with row radii the gradients go through peer_grads and only the parameter
+     * broadcast uses the multicast mapping. */
+    const int32_t* peer_row_radii[FB200_MAX_PEERS];
+    int32_t row_width[FB200_ADAM_MAX_GROUPS];   /* 0: the group has no row structure (always read) */
+    int32_t row_count;
 } fb200_adam_args;
 int fb200_adam_step(const fb200_adam_args* args, void* stream);
 
@@ -337,7 +361,7 @@ int64_t fb200_kernel_launches(void);
 
 const char* fb200_last_error(void);
 int fb200_abi_version(void);
-/* sizeof() of the ABI structs in declaration order {params, inputs, workspace, grads, extra, frosting_params,
+/* sizeof() of the ABI structs, in this order: {params, inputs, workspace, grads, extra, frosting_params,
  * frosting_grads, adam_args, layout}: lets a foreign-language binding verify its struct mirrors at load time. */
 #define FB200_ABI_STRUCTS 9
 int fb200_abi_struct_sizes(size_t* out /* [FB200_ABI_STRUCTS] */);

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTED) == names, "frosting_b200/_lib.py:EXPORTED out of sync with the header"
-    assert L.fb200_abi_version() == _lib.ABI_VERSION == 3
+    assert L.fb200_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_workspace_size_queries_are_host_only_and_monotonic():
@@ -71,6 +71,21 @@ def test_argument_errors_are_reported_without_touching_cuda():
     assert rc == -1 and b"exactly one of either scale/rotation pair" in L.fb200_last_error()
     with pytest.raises(_lib.Fb200Error):
         _lib.check(rc)
+    # frosting mode: the parameter block replaces the attribute pointers, it does not coexist with them
+    d = dummy
+    fp = _lib.FrostingParams(P=10, n_verts=4, n_faces=2, sh_rest=15, d_bary_logits=d, d_cells=d, d_faces=d, d_inner_verts=d,
+                             d_outer_verts=d, d_opacity_logits=d, d_log_scales=d, d_quats=d, d_sh_dc=d, d_sh_rest=d)
+    prm.sh_degree, prm.sh_coeffs = 3, 16
+    inp = _lib.Inputs(d_background=d, d_means3D=d, d_viewmatrix=d, d_projmatrix=d, d_campos=d, frosting=C.addressof(fp))
+    rc = L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws), None, None, None)
+    assert rc == -1 and b"frosting mode: the attribute / mask pointers" in L.fb200_last_error()
+    inp.d_means3D = None
+    prm.sh_coeffs = 9
+    rc = L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws), None, None, None)
+    assert rc == -1 and b"do not match the parameter block" in L.fb200_last_error()
+    prm.sh_coeffs = 16
+    rc = L.fb200_forward(C.byref(prm), C.byref(inp), C.byref(ws), None, None, None)
+    assert rc == -1 and b"workspace pointers missing" in L.fb200_last_error()      # got past the frosting checks
 
 
 def test_profile_and_launch_counter_entry_points():

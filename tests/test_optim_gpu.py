@@ -20,6 +20,57 @@ def _grads(t, rank, n):
     return g
 
 
+ROWS = 1001
+ROW_NAMES = [n for n, sh in SHAPES.items() if sh[0] == ROWS]
+
+
+def _radii(t, rank):
+    """Which of the ROWS rows rank `rank` 'rendered' at step t (about a quarter, in runs like a real frame)."""
+    rng = np.random.default_rng(77 * t + rank)
+    r = (rng.random(ROWS) < 0.25).astype(np.int32) * rng.integers(1, 40, ROWS).astype(np.int32)
+    r[100:300] = 0
+    r[rng.random(ROWS) < 0.05] = -1      # radii are signed: anything <= 0 is "not rendered"
+    return r
+
+
+def _sparse_grads(t, rank, name, n):
+    """Dense gradient of the step, what the slab holds (dead rows poisoned: they must never be read), and its radii."""
+    g = _grads(t, rank, n)
+    if name not in ROW_NAMES:
+        return g, g
+    radii = _radii(t, rank // 10 if rank >= 10 else 0)
+    w = n // ROWS
+    live = np.repeat(radii > 0, w)
+    dense = np.where(live, g, 0.0).astype(np.float32)
+    slab = np.where(live, g, np.nan).astype(np.float32)
+    return dense, slab
+
+
+def test_sparse_row_step_matches_the_dense_oracle():
+    """fb200_adam_args.peer_row_radii: rows with radii <= 0 are zero rows that are NOT read -- the slab holds NaN there."""
+    from frosting_b200 import optim
+    from oracle import adam as adam_oracle
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    init = {n: rng.standard_normal(s).astype(np.float32) for n, s in SHAPES.items()}
+    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(dev) for n, x in init.items()}, LRS, rows=ROWS)
+    assert opt.grads.accepts_row_radii and opt.slabs.row_width == [6, 3, 45, 1, 0, 4]
+    ora = {n: (init[n].reshape(-1).copy(), np.zeros(init[n].size, np.float32), np.zeros(init[n].size, np.float32))
+           for n in SHAPES}
+    for t in range(1, 6):
+        for k, n in enumerate(SHAPES):
+            dense, slab = _sparse_grads(t, k, n, init[n].size)
+            opt.grads[n].copy_(torch.from_numpy(slab).view(SHAPES[n]))
+            ora[n] = adam_oracle.adam_step(ora[n][0], dense, ora[n][1], ora[n][2], LRS[n], t)
+        opt.grads.rows_from(torch.from_numpy(_radii(t, 0)).to(dev), ROW_NAMES)
+        opt.step()
+        assert opt.grads.row_radii is None
+    for n in SHAPES:
+        got = opt.params[n].detach().cpu().numpy().reshape(-1)
+        assert np.isfinite(got).all(), n
+        np.testing.assert_allclose(got, ora[n][0], rtol=3e-6, atol=5e-7)
+
+
 def test_fused_adam_matches_oracle_and_torch():
     from frosting_b200 import optim
     from oracle import adam as adam_oracle
@@ -96,12 +147,43 @@ def test_grad_sink_receives_the_autograd_gradients():
     assert opt.update_learning_rate(15_000) == pytest.approx(np.sqrt(0.005 * 0.00005))
 
 
+def test_frosting_render_sparse_sink_step_equals_the_dense_step():
+    """frosting_render -> FrostingAdam without a dense gradient anywhere: the backward writes the rendered rows of the
+    optimizer's slab (poisoned with NaN beforehand), hands `radii` over, and the step equals the step on the dense copy."""
+    import frosting_b200 as fb
+    from frosting_b200 import scenes, optim
+    dev = torch.device("cuda:0")
+    P, W, H = 30_000, 240, 160
+    cam = scenes.make_camera(W, H, device=dev)
+    params, mesh = scenes.frosting_layer(P, cam, 5, n_faces_target=5000, device=dev, view_distance=4.5)
+    rs = scenes.settings_for(cam, 3, device=dev)
+    _, fv, _ = fb.rasterize_mesh(mesh["verts"], mesh["faces"], cam.full_proj_transform, H, W, mark_last_on_bg=True)
+    cot = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1)).to(dev)
+    a, b = optim.FrostingAdam.for_frosting(params), optim.FrostingAdam.for_frosting(params)
+    for step in range(2):
+        a.slabs.grad_slab.fill_(float("nan"))
+        color, radii = fb.frosting_render(a.params, mesh, rs, face_visible=fv, grad_sink=a.grads)
+        (color * cot).sum().backward()
+        assert a.grads.row_radii is not None and set(a.grads.sparse_names) == set(a.slabs.names)
+        live = radii > 0
+        assert 0 < int(live.sum()) < P
+        for n in a.slabs.names:
+            g = a.slabs.grads.get(n)                       # dict.get: does not touch the book-keeping
+            assert bool(torch.isfinite(g[live]).all()), n
+            assert bool(torch.isnan(g[~live]).all()), n    # unrendered rows really were not written
+            b.grads[n].copy_(torch.where(live.view(-1, *([1] * (g.dim() - 1))), g, torch.zeros_like(g)))
+        a.step(); b.step()
+        assert torch.equal(a.slabs.param_slab[:a.slabs.total].view(torch.int32), b.slabs.param_slab[:b.slabs.total].view(torch.int32))
+        assert torch.equal(a.exp_avg, b.exp_avg) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+        assert bool(torch.isfinite(a.slabs.param_slab).all())
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p
 
 
-def _peer_worker(rank, world, port, q, multicast):
+def _peer_worker(rank, world, port, q, multicast, sparse=False):
     import torch.distributed as dist
     from frosting_b200 import optim
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -111,12 +193,14 @@ def _peer_worker(rank, world, port, q, multicast):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     rng = np.random.default_rng(3)
     init = {n: rng.standard_normal(s).astype(np.float32) for n, s in SHAPES.items()}
-    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(dev) for n, x in init.items()}, LRS)
+    opt = optim.FrostingAdam({n: torch.from_numpy(x).to(dev) for n, x in init.items()}, LRS, rows=ROWS if sparse else None)
     loss_sum = None
     for t in range(1, 4):
         for k, n in enumerate(SHAPES):
-            g = _grads(t, 10 * rank + k, init[n].size)
+            g = _sparse_grads(t, 10 * rank + k, n, init[n].size)[1] if sparse else _grads(t, 10 * rank + k, init[n].size)
             opt.grads[n].copy_(torch.from_numpy(g).view(SHAPES[n]))
+        if sparse:
+            opt.grads.rows_from(torch.from_numpy(_radii(t, rank)).to(dev), ROW_NAMES)
         loss = torch.tensor([float(rank + 1)], device=dev)
         opt.step(loss=loss)
         loss_sum = float(loss)
@@ -127,14 +211,15 @@ def _peer_worker(rank, world, port, q, multicast):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="peer-memory step needs 2 GPUs")
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense", "sparse-rows"])
 @pytest.mark.parametrize("multicast", [False, True], ids=["peer-pointers", "nvswitch-multicast"])
-def test_peer_memory_dp_adam_world2(multicast):
+def test_peer_memory_dp_adam_world2(multicast, sparse):
     import torch.multiprocessing as mp
     from oracle import adam as adam_oracle
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q, multicast)) for r in range(world)]
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q, multicast, sparse)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -153,7 +238,8 @@ def test_peer_memory_dp_adam_world2(multicast):
         assert np.array_equal(res[0][n], res[1][n]), n          # replicas bit-identical
         p, m, v = init[n].reshape(-1).copy(), np.zeros(init[n].size, np.float32), np.zeros(init[n].size, np.float32)
         for t in range(1, 4):
-            gs = [_grads(t, 10 * r + k, init[n].size) for r in range(world)]
+            gs = [_sparse_grads(t, 10 * r + k, n, init[n].size)[0] if sparse else _grads(t, 10 * r + k, init[n].size)
+                  for r in range(world)]
             p, m, v = adam_oracle.dp_step(p, gs, m, v, LRS[n], t, 0.5)
         np.testing.assert_allclose(res[0][n], p, rtol=3e-6, atol=5e-7)
 

@@ -192,12 +192,14 @@ def test_frosting_render_equals_the_two_step_path(cuda_device):
     (color2 * cot).sum().backward()
     assert torch.equal(radii1, radii2) and 0 < int((radii1 > 0).sum()) < P
     assert torch.equal(color1.view(torch.int32), color2.view(torch.int32))
+    # the two frames' blend backwards accumulate with float atomics in different orders: typically 1e-6 of the tensor's
+    # scale, but the scale / rotation gradients cancel large terms -- tools/dbg_frost.py saw 1.7e-4 once in 60 repeats
     for k in p1:
         m, frac = rel_err_stats(p1[k].grad, p2[k].grad)
-        assert m <= 1e-4, (k, m)
+        assert m <= 1e-3 and frac <= 1e-3, (k, m, frac)
     for k in ("inner", "outer"):
         m, frac = rel_err_stats(m1[k].grad, m2[k].grad)
-        assert m <= 1e-4, (k, m)
+        assert m <= 1e-3, (k, m)
     # (b) against Frosting's torch property chain (frosting_model.py:713-799) + mask tensor: the attribute values agree
     # to ~1 ulp, which flips a handful of alpha >= 1/255 / tile-rect decisions -- statistical comparison
     p3 = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
@@ -216,6 +218,47 @@ def test_frosting_render_equals_the_two_step_path(cuda_device):
     dead = radii1 <= 0
     for k in p1:
         assert float(p1[k].grad[dead].abs().sum()) == 0.0, k
+
+
+def test_frosting_mode_equals_the_attribute_kernel_route(cuda_device):
+    """Row f1 proper: `frosting_render` (the rasterizer reads the parameters itself, nothing materialised, parameter
+    gradients written by the per-Gaussian backward for rendered rows only) against `frosting_render_two_step` (attribute
+    kernel -> rasterizer -> attribute backward): bit-identical image and radii, gradients equal up to the order of the
+    blend backward's float atomics; the optimizer-sink route gives the same numbers as the autograd route."""
+    dev = cuda_device
+    for (W, H, P, faces, occl) in ((320, 200, 50_000, 8000, True), (200, 120, 3001, 500, False)):
+        cam = scenes.make_camera(W, H, device=dev)
+        params, mesh = scenes.frosting_layer(P, cam, 11, n_faces_target=faces, device=dev, view_distance=4.5)
+        rs = scenes.settings_for(cam, 3, device=dev)
+        fv = None
+        if occl:
+            _, fv, _ = fb.rasterize_mesh(mesh["verts"], mesh["faces"], cam.full_proj_transform, H, W, mark_last_on_bg=True)
+        cot = torch.randn(3, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
+        res = []
+        for fn in (fb.frosting_render, fb.frosting_render_two_step):
+            p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+            m = dict(mesh); m["inner"] = mesh["inner"].clone().requires_grad_(True); m["outer"] = mesh["outer"].clone().requires_grad_(True)
+            color, radii = fn(p, m, rs, face_visible=fv)
+            (color * cot).sum().backward()
+            res.append((color, radii, p, m))
+        (c1, r1, p1, m1), (c2, r2, p2, m2) = res
+        assert torch.equal(r1, r2) and 0 < int((r1 > 0).sum()) <= P
+        assert torch.equal(c1.view(torch.int32), c2.view(torch.int32))
+        for k in p1:
+            mx, frac = rel_err_stats(p1[k].grad, p2[k].grad)
+            assert mx <= 1e-3 and frac <= 1e-3, (k, mx, frac)     # atomic-order noise of two blend backwards, see above
+            assert float(p1[k].grad[r1 <= 0].abs().sum()) == 0.0, k
+        for k in ("inner", "outer"):
+            mx, _ = rel_err_stats(m1[k].grad, m2[k].grad)
+            assert mx <= 1e-3, (k, mx)
+        # gradients straight into a caller-owned sink (dirty on entry: rows of unrendered Gaussians must come out zero)
+        sink = {k: torch.full_like(v, 7.0) for k, v in params.items()}
+        p3 = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        color, radii = fb.frosting_render(p3, mesh, rs, face_visible=fv, grad_sink=sink)
+        (color * cot).sum().backward()
+        for k in p1:
+            mx, _ = rel_err_stats(sink[k].view_as(p1[k].grad), p1[k].grad)
+            assert mx <= 1e-3 and p3[k].grad is None, (k, mx)
 
 
 def test_fused_attribute_kernels_against_reference_property_goldens(cuda_device):
