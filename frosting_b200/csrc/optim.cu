@@ -71,6 +71,12 @@ adam_shard_kernel(const fb200_adam_args a) {
         if (lr < 0.f) continue;        // group without a gradient this step: untouched, like a torch parameter with .grad None
         const float step = lr / a.bias_correction1;
 
+        // the rank's own state first: these loads do not depend on anything below and overlap the (dependent) radii ->
+        // gradient chain of the masked path
+        const int64_t li = i - v_lo;
+        float4 m = mom1[li], v = mom2[li];
+        float4 p = reinterpret_cast<const float4*>(a.peer_params[a.rank])[i];
+
         // gradient: one 128-bit load per peer, all issued before the first use
         float4 g[kPeers];
         const uint32_t w = kMasked ? (uint32_t)a.row_width[k] : 0u;
@@ -115,9 +121,6 @@ adam_shard_kernel(const fb200_adam_args a) {
             if (p < a.world) { s.x += g[p].x; s.y += g[p].y; s.z += g[p].z; s.w += g[p].w; }
         s.x *= a.grad_scale; s.y *= a.grad_scale; s.z *= a.grad_scale; s.w *= a.grad_scale;
 
-        const int64_t li = i - v_lo;
-        float4 m = mom1[li], v = mom2[li];
-        float4 p = reinterpret_cast<const float4*>(a.peer_params[a.rank])[i];
         p.x = adam1(s.x, m.x, v.x, p.x, step, c);
         p.y = adam1(s.y, m.y, v.y, p.y, step, c);
         p.z = adam1(s.z, m.z, v.z, p.z, step, c);

@@ -50,6 +50,12 @@ BWD_PAIR_KERNEL = os.environ.get("FB200_BWD_PAIR", "0") == "1"
 FWD_TMA = os.environ.get("FB200_FWD_TMA", "0") == "1"
 ZERO_OVERLAP = os.environ.get("FB200_ZERO_OVERLAP", "0") == "1"   # A/B: dense zero rows on a side stream under the blend bwd (bit 5)
 BWD_OCC24 = os.environ.get("FB200_BWD_OCC24", "0") == "1"      # A/B: backward blend at 24 resident warps / SM (debug bit 4)
+# FB200_CHECK_BEFORE_BACKWARD=1: wait for a speculatively launched forward's status words before launching its backward
+# (an overflow is then raised from backward()).  Default: no wait -- the backward is enqueued behind the forward at once
+# (its kernels exit on the overflow word; the gradients of such a frame are zeros) and the overflow is raised by the next
+# call on this host thread.  The wait cost the GPU an idle gap per frame: the host slept until the forward had finished
+# and only then started enqueueing the loss / backward kernels (1.4 of 2.0 ms of a training iteration's host time).
+CHECK_BEFORE_BACKWARD = os.environ.get("FB200_CHECK_BEFORE_BACKWARD", "0") == "1"
 _HEADROOM = 2.0           # speculative capacity = _HEADROOM x (largest count seen for this problem size) + 64 Ki
 _RING = 8                 # status mailboxes in flight per (thread, device)
 
@@ -67,6 +73,20 @@ def _sizes(L, P, W, H):
             _size_cache.clear()
         _size_cache[k] = v
     return v
+
+
+def _grow_hint(hint: int, num_rendered: int) -> int:
+    """Capacity to launch the next frame of this size with.  It moves rarely and in coarse steps: every distinct capacity
+    is a distinct allocation size for torch's caching allocator, and a fresh 100+ MB cudaMalloc stalls the stream for
+    milliseconds (a training run whose instance count creeps upward re-allocated every few frames: 30 ms hiccups).
+    Grow only when less than 25 % of the headroom is left, then to `_HEADROOM` x the count, rounded up to 1/8 of its
+    leading power of two."""
+    n = max(int(num_rendered), 0)
+    if hint > 0 and n * 1.25 <= hint:
+        return hint
+    want = int(n * _HEADROOM) + 65536
+    step = 1 << max(want.bit_length() - 4, 16)
+    return max(hint, (want + step - 1) // step * step)
 
 
 class BinningOverflow(RuntimeError):
@@ -119,9 +139,7 @@ class _HostState:
             if p in self.pending:
                 self.pending.remove(p)
             self.last_num_rendered = p.num_rendered
-            want = int(max(p.num_rendered, 0) * _HEADROOM) + 65536
-            if want > self.hints.get(p.key, 0):
-                self.hints[p.key] = want
+            self.hints[p.key] = _grow_hint(self.hints.get(p.key, 0), p.num_rendered)
         if p.overflow and not p.reported:
             p.reported = True
             raise BinningOverflow(
@@ -293,8 +311,8 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
     Default: ONE-PHASE, no host wait.  `fb200_forward` is launched with a binning capacity speculated from earlier frames
     of this problem size (2x the largest count seen); the frame's status words travel to a pinned mailbox behind the
     kernels and are looked at lazily -- by a later call on this thread, or before this frame's backward.  An overflow
-    (never silently wrong: the kernels exit on the overflow word) raises BinningOverflow and the next frame of this
-    size is sized from the count that overflowed.  The FIRST frame of a problem size, `debug`, `exact=True` and
+    (never silently wrong: the kernels, the backward's included, exit on the overflow word) raises BinningOverflow from
+    the next call on this thread and the next frame of this size is sized from the count that overflowed.  The FIRST frame of a problem size, `debug`, `exact=True` and
     FB200_EXACT_BINNING=1 take the two-phase path: preprocess + tile scan, host reads the exact count (the reference
     blocks at the same point, rasterizer_impl.cu:280-281), raster phase with an exactly sized buffer.
     """
@@ -352,7 +370,7 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
                 _lib.check(L.fb200_forward_raster(C.byref(prm), C.byref(inp), C.byref(ws),
                                                   C.c_void_p(out_color.data_ptr()), rptr, sptr))
                 ws.h_status = None
-            host.hints[key] = max(hint, int(num_rendered * _HEADROOM) + 65536)
+            host.hints[key] = _grow_hint(hint, num_rendered)
             host.last_num_rendered = num_rendered
         else:
             capacity = hint
@@ -382,7 +400,8 @@ def _launch_forward(means3D, sh, colors_precomp, opacities, scales, rotations, c
 def _launch_backward(call: "_Call", radii, grad_out_color, grad_out_extra=None, sparse_rows=False,
                      frosting_grads=None):
     L = _lib.lib()
-    call.check()       # a speculatively launched forward that overflowed has no state to differentiate: raise
+    if CHECK_BEFORE_BACKWARD:
+        call.check()       # a speculatively launched forward that overflowed has no state to differentiate: raise here
     prm = call.prm
     P, M = prm.P, prm.sh_coeffs
     device = call.device

@@ -39,14 +39,32 @@ def test_speculative_forward_equals_exact_and_overflow_is_loud(cuda_device):
         assert rel_err_stats(g1[k], g0[k])[0] <= 1e-4, k
     R = fbr.last_num_rendered(dev)
     assert R > 1000
-    # force an overflow: pretend earlier frames of this size were almost empty
+    # force an overflow: pretend earlier frames of this size were almost empty.  The frame's backward is enqueued without
+    # waiting for its status words (every kernel of the frame exits on the overflow word: its gradients are zeros) and the
+    # NEXT call on this thread raises
     host.hints[(P, W, H)] = R // 2
+    (_cx, _rx), gx = _fwd_bwd(rs, g, cot)
+    torch.cuda.synchronize(dev)
+    for k in gx:
+        assert float(gx[k].abs().sum()) == 0.0, k
     with pytest.raises(fbr.BinningOverflow):
-        _fwd_bwd(rs, g, cot)                        # raised before the overflowed frame's backward is launched
+        _fwd_bwd(rs, g, cot)
     assert host.hints[(P, W, H)] >= R                # the count that overflowed sized the next frame
     (c2, r2), g2 = _fwd_bwd(rs, g, cot)
     assert torch.equal(c0.view(torch.int32), c2.view(torch.int32))
+    # FB200_CHECK_BEFORE_BACKWARD=1: the overflow is raised from the frame's own backward (one host wait per frame)
+    fbr.last_num_rendered(dev)                       # look at every earlier frame first (they would re-grow the hint)
+    host.hints[(P, W, H)] = R // 2
+    fbr.CHECK_BEFORE_BACKWARD = True
+    try:
+        with pytest.raises(fbr.BinningOverflow):
+            _fwd_bwd(rs, g, cot)
+    finally:
+        fbr.CHECK_BEFORE_BACKWARD = False
+    (c3, r3), g3 = _fwd_bwd(rs, g, cot)
+    assert torch.equal(c0.view(torch.int32), c3.view(torch.int32))
     # an overflow nobody differentiates is reported by the next call on this thread
+    fbr.last_num_rendered(dev)
     host.hints[(P, W, H)] = R // 2
     with torch.no_grad():
         fb.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=g["shs"],
