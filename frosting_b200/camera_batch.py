@@ -58,24 +58,43 @@ def reduce_loss(local_loss: torch.Tensor, group=None) -> torch.Tensor:
 class LossReducer:
     """The path's only collective, kept off the critical path.
 
-    Every frame's scalar loss is summed over the ranks by its own asynchronous all-reduce: the collective is ordered
-    after the frame's loss on the device (the process group's stream waits for the current stream at enqueue) but
-    the COMPUTE stream never waits for it, so a slow rank delays nobody's next frame; results are collected when
-    `collect()` is called (every K frames or at the end), which is the only point that joins the two streams.
-    """
+    Every frame's scalar loss is summed over the ranks, `every` frames per collective: a frame's loss is copied into a
+    device buffer (stream-ordered, no host involvement) and each full buffer goes out as ONE asynchronous all-reduce.
+    The collective is ordered after the buffered losses on the device (the process group's stream waits for the current
+    stream at enqueue) but the COMPUTE stream never waits for it, so a slow rank delays nobody's next frame; results are
+    collected when `collect()` is called, the only point that joins the two streams.
 
-    def __init__(self, group=None):
+    Why batched: a 4-byte all-reduce per frame is cheap on the wire but not on the SMs -- its kernel spins until the
+    slowest rank's arrives, and with nothing idle on the GPU any more (no host wait between a frame's forward and
+    backward) that spinning comes out of the blend kernels: 8 ranks, 1.19 vs 1.02 ms per frame.  One collective per
+    `every` frames divides it by `every`."""
+
+    def __init__(self, group=None, every=8):
         self.group = group
         self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.every = max(int(every), 1)
+        self.buf, self.fill = None, 0
         self.pending = []
 
+    def _flush(self):
+        if self.fill == 0:
+            return
+        part = self.buf[:self.fill]
+        work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if self.on else None
+        self.pending.append((part, work))
+        self.buf, self.fill = None, 0
+
     def add(self, loss: torch.Tensor):
-        buf = loss.detach().reshape(1).clone()
-        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if self.on else None
-        self.pending.append((buf, work))
+        if self.buf is None:
+            self.buf = torch.empty(self.every, dtype=torch.float32, device=loss.device)
+        self.buf[self.fill].copy_(loss.detach().reshape(()))
+        self.fill += 1
+        if self.fill == self.every:
+            self._flush()
 
     def collect(self):
-        """Reduced losses of every frame added since the last collect, as one tensor (device)."""
+        """Reduced losses of every frame added since the last collect, in order, as one tensor (device)."""
+        self._flush()
         out = []
         for buf, work in self.pending:
             if work is not None:

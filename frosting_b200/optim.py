@@ -189,7 +189,10 @@ class FlatSlabs:
         self.params, self.grads = {}, GradSink()
         self.row_radii = None
         if self.rows:
-            self.grads.accepts_row_radii = True
+            # sparse gradient rows pay off on the local and peer-pointer paths (a peer's vector is fetched only where it
+            # rendered something); the in-switch sum cannot skip rows and beats masked peer loads from 4 ranks up
+            # (8 ranks: step ~1.1 ms in the switch vs ~1.5 ms masked) -- there the producer zero-fills instead
+            self.grads.accepts_row_radii = not (self.mc_params and self.mc_grads)
             self.row_radii = self.grad_slab[self.total:self.total + self.rows].view(torch.int32)
         for n, s in zip(names, self.starts):
             k = tensors[n].numel()
