@@ -550,8 +550,8 @@ def main():
         "config": {
             "workload": cb.WORKLOAD_TEXT[args.workload] + ring_txt,
             "gaussians": P, "image": f"{W}x{H}", "sh_degree": wl["D"], "cameras_per_gpu": cb.CAMS_PER_GPU,
-            "parallelism": f"camera-batch x{world} (Gaussians replicated, NCCL all-reduce of the scalar loss, "
-                           "asynchronous per frame)",
+            "parallelism": f"camera-batch x{world} (Gaussians replicated, asynchronous NCCL all-reduce of the frames' "
+                           "scalar losses, 8 frames per collective)",
             "frame": "occlusion culling (visible-face lookup inside preprocess) + rasterizer forward + (color*G).sum() + "
                      "backward to all attributes",
             "l2": "inputs larger than L2: ~236 B x P of attributes read per frame, no flush needed",

@@ -110,3 +110,45 @@ def test_camera_block_partition():
     with pytest.raises(ValueError):
         sharding.camera_block(2, 2, 8)
     assert float(sharding.reduce_loss(torch.tensor(3.0))) == 3.0   # no process group: identity
+
+
+def test_capacity_hint_moves_rarely_and_in_coarse_steps():
+    """`_grow_hint` (frosting_b200/rasterizer.py): every distinct capacity is a distinct allocation size, so the hint has
+    hysteresis (untouched while >= 20 % headroom is left) and a coarse grid (1/8 of the leading power of two)."""
+    from frosting_b200.rasterizer import _grow_hint, _HEADROOM
+    h = _grow_hint(0, 1_000_000)
+    assert h >= _HEADROOM * 1_000_000 and h % (1 << 17) == 0
+    assert _grow_hint(h, 1_200_000) == h                      # creeping counts do not move it
+    assert _grow_hint(h, int(0.8 * h)) == h
+    h2 = _grow_hint(h, int(0.8 * h) + 1)                      # less than 20 % headroom left: grows, to 2x the count
+    assert h2 > h and h2 >= 2 * (int(0.8 * h) + 1)
+    assert _grow_hint(h2, 10) == h2                           # never shrinks
+    sizes = {_grow_hint(0, n) for n in range(900_000, 1_100_000, 1000)}
+    assert len(sizes) <= 3                                    # neighbouring counts share an allocation size
+    assert _grow_hint(0, 0) >= 65536 and _grow_hint(0, -5) >= 65536
+
+
+def test_grad_sink_row_bookkeeping():
+    """GradSink (frosting_b200/optim.py): fetching a view marks the group written; sparse-row producers hand `radii` over
+    only to sinks that declared row structure; `clear()` forgets both."""
+    import torch
+    from frosting_b200.optim import GradSink, slab_layout
+    k = GradSink(a=torch.zeros(4, 3), b=torch.zeros(4))
+    assert not k.written and k.row_radii is None
+    _ = k["a"]
+    assert k.written == {"a"} and k.get("b") is not None and k.written == {"a"}      # dict.get does not mark
+    import pytest
+    with pytest.raises(RuntimeError):
+        k.rows_from(torch.ones(4, dtype=torch.int32), ["a"])                          # no row structure declared
+    k.accepts_row_radii = True
+    r = torch.tensor([1, 0, -1, 5], dtype=torch.int32)
+    k.rows_from(r, ["a"])
+    assert k.row_radii is r and k.sparse_names == {"a"}
+    k.sink_once(["a"])
+    with pytest.raises(RuntimeError):
+        k.sink_once(["a", "b"])                                                       # a second overwrite before the step
+    k.clear()
+    assert not k.written and not k.sunk and k.row_radii is None and not k.sparse_names
+    # the radii region sits behind the Adam range of the slab, 16-byte aligned
+    starts, total = slab_layout([12, 4], world=2)
+    assert total % 8 == 0 and starts == [0, 12, 16]

@@ -23,12 +23,19 @@ def _worker(rank, world, port, q):
     total = sharding.reduce_loss(local)
     t = torch.tensor([1.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)             # the max-over-ranks timing reduction of bench.py
-    # the per-frame loss reduction of CameraBatch.run: one asynchronous all-reduce per frame, collected every K frames
+    # the per-frame loss reduction of CameraBatch.run: the frames' losses are buffered and go out `every` frames per
+    # asynchronous all-reduce; whatever the batch size, frame k comes back as the sum of every rank's frame k, in order
     red = sharding.LossReducer()
     for c in cams:
         red.add(torch.tensor(float((c + 1) ** 2)))
     per_frame = red.collect().tolist()
     assert red.collect().numel() == 0
+    for every in (1, 3):                                 # a partial last batch is flushed by collect()
+        red = sharding.LossReducer(every=every)
+        for c in cams:
+            red.add(torch.tensor(float((c + 1) ** 2)))
+        assert len(red.pending) == len(cams) // every
+        assert red.collect().tolist() == per_frame
     q.put((rank, cams, float(local), float(total), float(t), per_frame))
     dist.destroy_process_group()
 
