@@ -206,7 +206,8 @@ class _Call:
         return self._num_rendered
 
     def check(self):
-        """Raise if this frame overflowed its binning capacity (called before its backward is launched)."""
+        """Raise if this frame overflowed its binning capacity (waits for its status words; called before the backward is
+        launched only under FB200_CHECK_BEFORE_BACKWARD=1)."""
         if self.pending is not None:
             self.host.resolve(self.pending)
 
