@@ -100,7 +100,9 @@ typedef struct fb200_frosting_params {
                                         unwritten: fb200_grads.sparse_rows) */
 } fb200_frosting_params;
 
-typedef struct fb200_frosting_grads {      /* all fully written; inner/outer vertex gradients are accumulated */
+typedef struct fb200_frosting_grads {      /* fb200_frosting_attributes_backward: all fully written; frosting mode of
+                                            * fb200_backward: rows of rendered Gaussians only.  Inner / outer vertex gradients
+                                            * are accumulated (cleared by the call first) */
     float* d_bary_logits; float* d_inner_verts; float* d_outer_verts; float* d_opacity_logits;
     float* d_log_scales; float* d_quats; float* d_sh_dc; float* d_sh_rest;
 } fb200_frosting_grads;
@@ -199,7 +201,8 @@ int fb200_forward_raster(const fb200_params* prm, const fb200_inputs* in, const 
                          float* d_out_color, int32_t* d_radii, void* stream);
 
 /* Gradient outputs of the backward pass, shapes as DGR/rasterize_points.cu:151-159.
- * All are fully written by the call (invisible Gaussians get zeros); no pre-zeroing needed. */
+ * All are fully written by the call (invisible Gaussians get zeros) unless sparse_rows / frosting say otherwise; no
+ * pre-zeroing needed. */
 typedef struct fb200_grads {
     float* d_dL_dmeans2D;     /* [P,3] (z = 0) */
     float* d_dL_dcolors;      /* [P,3]; may be NULL when colours come from SH (then an intermediate, not written) */
